@@ -1,0 +1,250 @@
+// Single-pass loss kernels: value + analytic gradient (clip_diffusion/losses.py:10-35).
+// HBM-bound: read x once (neighbours come from L1/L2), write grad once.
+#include "common.cuh"
+
+namespace {
+
+// ---- total variation (losses.py:20-28) ---------------------------------------------------------
+// One thread per 4 consecutive pixels of a row; neighbours via direct (cached) loads.
+__global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, int C, int H, int W, float gscale,
+                                                 int accumulate, float* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ float red[32];
+  const int b = blockIdx.y;
+  const int64_t plane = (int64_t)H * W;
+  const int64_t per_img = plane * C;
+  const float* xb = x + b * per_img;
+  float* gb = grad ? grad + b * per_img : nullptr;
+  const float inv = 1.0f / (float)per_img;
+  const float gs = 2.0f * gscale * inv;
+  const int W4 = (W + 3) >> 2;
+  const int64_t nvec = (int64_t)C * H * W4;
+  float acc = 0.f;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const int xv = (int)(v % W4);
+    const int64_t row = v / W4;  // c*H + h
+    const int h = (int)(row % H);
+    const int x0 = xv << 2;
+    const float* r = xb + row * W;
+    float cur[6];  // x[x0-1 .. x0+4]
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int xx = x0 - 1 + i;
+      cur[i] = (xx >= 0 && xx < W) ? __ldg(r + xx) : 0.f;
+    }
+    float up[4], dn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xx = x0 + i;
+      const bool ok = xx < W;
+      up[i] = (ok && h > 0) ? __ldg(r - W + xx) : 0.f;
+      dn[i] = (ok && h + 1 < H) ? __ldg(r + W + xx) : 0.f;
+    }
+    float g[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xx = x0 + i;
+      if (xx >= W) { g[i] = 0.f; continue; }
+      const float c = cur[i + 1];
+      const float dx = (xx + 1 < W) ? cur[i + 2] - c : 0.f;   // replicate pad => 0 at the last column
+      const float dy = (h + 1 < H) ? dn[i] - c : 0.f;
+      const float dxl = (xx > 0) ? c - cur[i] : 0.f;           // dx of the left neighbour
+      const float dyu = (h > 0) ? c - up[i] : 0.f;             // dy of the upper neighbour
+      acc += dx * dx + dy * dy;
+      g[i] = gs * (dxl + dyu - dx - dy);
+    }
+    if (gb) {
+      float* o = gb + row * W + x0;
+      if (x0 + 3 < W && ((W & 3) == 0)) {
+        float4 w = make_float4(g[0], g[1], g[2], g[3]);
+        if (accumulate) { const float4 p = *reinterpret_cast<float4*>(o); w.x += p.x; w.y += p.y; w.z += p.z; w.w += p.w; }
+        *reinterpret_cast<float4*>(o) = w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (x0 + i < W) o[i] = (accumulate ? o[i] : 0.f) + g[i];
+      }
+    }
+  }
+  if (loss) {
+    const float t = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(loss + b, t * inv);
+  }
+}
+
+// ---- rgb range (losses.py:31-35) -----------------------------------------------------------------
+__global__ void __launch_bounds__(256) range_kernel(const float* __restrict__ x, int64_t per_img, float gscale, int accumulate,
+                                                    float* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ float red[32];
+  const int b = blockIdx.y;
+  const float* xb = x + b * per_img;
+  float* gb = grad ? grad + b * per_img : nullptr;
+  const float inv = 1.0f / (float)per_img;
+  const float gs = 2.0f * gscale * inv;
+  float acc = 0.f;
+  const int64_t n4 = per_img >> 2;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (int64_t)gridDim.x * blockDim.x) {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(xb) + v);
+    float e[4] = {p.x, p.y, p.z, p.w};
+    float g[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float d = e[i] - fminf(fmaxf(e[i], -1.f), 1.f);
+      acc += d * d;
+      g[i] = gs * d;
+    }
+    if (gb) {
+      float4 w = make_float4(g[0], g[1], g[2], g[3]);
+      float4* o = reinterpret_cast<float4*>(gb) + v;
+      if (accumulate) { const float4 q = *o; w.x += q.x; w.y += q.y; w.z += q.z; w.w += q.w; }
+      *o = w;
+    }
+  }
+  // tail (per_img not a multiple of 4)
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = xb[i] - fminf(fmaxf(xb[i], -1.f), 1.f);
+    acc += d * d;
+    if (gb) gb[i] = (accumulate ? gb[i] : 0.f) + gs * d;
+  }
+  if (loss) {
+    const float t = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(loss + b, t * inv);
+  }
+}
+
+// ---- squared spherical distance (losses.py:10-16) -----------------------------------------------
+// One warp per (n, p) pair for fwd / per n for bwd.  E <= 4096.
+__device__ __forceinline__ float sph_from_r(float r) {
+  const float a = asinf(0.5f * r);
+  return 2.f * a * a;
+}
+// d dist / d r  divided by r (r > 0)
+__device__ __forceinline__ float sph_dr_over_r(float r) {
+  const float h = 0.5f * r;
+  const float a = asinf(h);
+  return 2.f * a / (sqrtf(fmaxf(1.f - h * h, 0.f)) * r);
+}
+
+__global__ void __launch_bounds__(128) sph_fwd_kernel(const float* __restrict__ emb, const float* __restrict__ txt, int N, int P, int E,
+                                                      float* __restrict__ dist) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N * P) return;
+  const int n = warp / P, p = warp % P;
+  const float* x = emb + (int64_t)n * E;
+  const float* y = txt + (int64_t)p * E;
+  float sx = 0.f, sy = 0.f;
+  for (int e = lane; e < E; e += 32) { sx += x[e] * x[e]; sy += y[e] * y[e]; }
+  sx = warp_sum(sx); sy = warp_sum(sy);
+  const float ix = 1.f / fmaxf(sqrtf(sx), 1e-12f), iy = 1.f / fmaxf(sqrtf(sy), 1e-12f);
+  float r2 = 0.f;
+  for (int e = lane; e < E; e += 32) { const float u = x[e] * ix - y[e] * iy; r2 += u * u; }
+  r2 = warp_sum(r2);
+  if (lane == 0) dist[warp] = sph_from_r(sqrtf(r2));
+}
+
+// demb[n,:] = sum_p g[n,p] * d dist[n,p] / d emb[n,:];  g given explicitly (gdist) or as coef*w[p].
+// Optionally accumulates loss = sum g*dist into loss_out (fused form).
+__global__ void __launch_bounds__(128) sph_bwd_kernel(const float* __restrict__ emb, const float* __restrict__ txt,
+                                                      const float* __restrict__ gdist, const float* __restrict__ w, float coef,
+                                                      int N, int P, int E, float* __restrict__ demb, float* __restrict__ loss_out) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* x = emb + (int64_t)n * E;
+  float sx = 0.f;
+  for (int e = lane; e < E; e += 32) sx += x[e] * x[e];
+  sx = warp_sum(sx);
+  const float nx = sqrtf(sx);
+  const float ix = 1.f / fmaxf(nx, 1e-12f);
+  const bool clampd = nx < 1e-12f;  // F.normalize's eps branch: x/eps is linear in x
+  float* o = demb + (int64_t)n * E;
+  for (int e = lane; e < E; e += 32) o[e] = 0.f;
+  float lsum = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const float* y = txt + (int64_t)p * E;
+    float sy = 0.f;
+    for (int e = lane; e < E; e += 32) sy += y[e] * y[e];
+    sy = warp_sum(sy);
+    const float iy = 1.f / fmaxf(sqrtf(sy), 1e-12f);
+    float r2 = 0.f, xu = 0.f;
+    for (int e = lane; e < E; e += 32) {
+      const float xh = x[e] * ix;
+      const float u = xh - y[e] * iy;
+      r2 += u * u;
+      xu += xh * u;
+    }
+    r2 = warp_sum(r2); xu = warp_sum(xu);
+    const float r = sqrtf(r2);
+    const float g = gdist ? gdist[(int64_t)n * P + p] : coef * (w ? w[p] : 1.f);
+    lsum += g * sph_from_r(r);
+    if (r > 0.f) {
+      const float k = g * sph_dr_over_r(r) * ix;
+      for (int e = lane; e < E; e += 32) {
+        const float xh = x[e] * ix;
+        const float u = xh - y[e] * iy;
+        o[e] += k * (clampd ? u : (u - xh * xu));
+      }
+    }
+  }
+  if (loss_out && lane == 0) atomicAdd(loss_out, lsum);
+}
+
+}  // namespace
+
+static int grid_for(int64_t work_items, int threads) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)CG_NUM_SMS * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+extern "C" int cg_tv_loss_fwd_bwd(const float* x, int B, int C, int H, int W, float grad_scale, int accumulate, float* loss,
+                                  float* grad, void* stream) {
+  CG_REQUIRE(x && B > 0 && C > 0 && H > 0 && W > 0, "cg_tv_loss_fwd_bwd: bad arguments");
+  cudaStream_t s = cg_stream(stream);
+  if (loss) CG_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * B, s));
+  const int64_t nvec = (int64_t)C * H * ((W + 3) / 4);
+  dim3 grid(grid_for(nvec, 256), B);
+  tv_kernel<<<grid, 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cg_range_loss_fwd_bwd(const float* x, int B, int C, int H, int W, float grad_scale, int accumulate, float* loss,
+                                     float* grad, void* stream) {
+  CG_REQUIRE(x && B > 0 && C > 0 && H > 0 && W > 0, "cg_range_loss_fwd_bwd: bad arguments");
+  const int64_t per_img = (int64_t)C * H * W;
+  CG_REQUIRE((per_img & 3) == 0 || B == 1, "cg_range_loss_fwd_bwd: C*H*W must be a multiple of 4 when B > 1");
+  CG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)grad & 15) == 0, "cg_range_loss_fwd_bwd: pointers must be 16-byte aligned");
+  cudaStream_t s = cg_stream(stream);
+  if (loss) CG_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * B, s));
+  dim3 grid(grid_for(per_img / 4 + 1, 256), B);
+  range_kernel<<<grid, 256, 0, s>>>(x, per_img, grad_scale, accumulate, loss, grad);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cg_spherical_dist_fwd(const float* emb, const float* txt, int N, int P, int E, float* dist, void* stream) {
+  CG_REQUIRE(emb && txt && dist && N > 0 && P > 0 && E > 0, "cg_spherical_dist_fwd: bad arguments");
+  const int warps = N * P;
+  sph_fwd_kernel<<<(warps + 3) / 4, 128, 0, cg_stream(stream)>>>(emb, txt, N, P, E, dist);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cg_spherical_dist_bwd(const float* emb, const float* txt, const float* gdist, int N, int P, int E, float* demb,
+                                     void* stream) {
+  CG_REQUIRE(emb && txt && gdist && demb && N > 0 && P > 0 && E > 0, "cg_spherical_dist_bwd: bad arguments");
+  sph_bwd_kernel<<<(N + 3) / 4, 128, 0, cg_stream(stream)>>>(emb, txt, gdist, nullptr, 0.f, N, P, E, demb, nullptr);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cg_spherical_loss_fwd_bwd(const float* emb, const float* txt, const float* w, int N, int P, int E, float coef,
+                                         float* loss_out, float* demb, void* stream) {
+  CG_REQUIRE(emb && txt && demb && N > 0 && P > 0 && E > 0, "cg_spherical_loss_fwd_bwd: bad arguments");
+  sph_bwd_kernel<<<(N + 3) / 4, 128, 0, cg_stream(stream)>>>(emb, txt, nullptr, w, coef, N, P, E, demb, loss_out);
+  CG_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,173 @@
+/*
+ * clipguide_b200 -- C ABI of the B200-native CLIP-guidance hot path.
+ *
+ * The reference (Penguin-jpg/clip-diffusion) has no FFI/plugin registry: its "operator API"
+ * for this path is a handful of Python functions plus torch autograd.
+ * Each entry point below is the device-side replacement of one of those functions; the
+ * reference file:line it replaces is cited per function.  The Python mirror of the reference
+ * interface lives in clip_diffusion_b200/ and binds this library with ctypes.
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes, no torch types.  Pointers are DEVICE pointers unless the
+ *     name ends in _h (host).  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - every function returns 0 on success, a negative CG_E* code on bad arguments, or a positive
+ *     cudaError_t; cg_last_error() gives a human readable message for the calling thread.
+ *   - nothing allocates: callers own all buffers (workspace sizes are queried first).
+ *   - all kernels are compiled for sm_100a only; there is no CPU fallback.
+ */
+#ifndef CLIPGUIDE_B200_H
+#define CLIPGUIDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_EINVAL (-1)
+#define CG_ENOSPC (-2)
+#define CG_EARCH (-3)
+
+const char* cg_last_error(void);
+/* ABI version of this header; bumps when a signature changes. */
+int cg_abi_version(void);
+/* 0 if the current device is sm_100; CG_EARCH otherwise. */
+int cg_check_device(void);
+
+/* ------------------------------------------------------------------ losses ---------------- */
+
+/* total_variational_loss, clip_diffusion/losses.py:20-28 -- value and analytic gradient in one pass.
+ *   x [B,C,H,W] fp32.  loss[b] = mean_{c,h,w}(dx^2 + dy^2) (replicate pad => last col/row differences 0).
+ *   grad (may be NULL) [B,C,H,W]: grad = (accumulate ? grad : 0) + grad_scale * d loss[b] / d x.
+ *   loss (may be NULL) [B] is overwritten. */
+int cg_tv_loss_fwd_bwd(const float* x, int B, int C, int H, int W, float grad_scale, int accumulate,
+                       float* loss, float* grad, void* stream);
+
+/* rgb_range_loss, clip_diffusion/losses.py:31-35.  Same calling convention as cg_tv_loss_fwd_bwd. */
+int cg_range_loss_fwd_bwd(const float* x, int B, int C, int H, int W, float grad_scale, int accumulate,
+                          float* loss, float* grad, void* stream);
+
+/* square_spherical_distance_loss, clip_diffusion/losses.py:10-16 (with L2_norm, utils/functional.py:74-76).
+ *   emb [N,E], txt [P,E] fp32 (un-normalised).  dist [N,P] = 2*asin(||emb^ - txt^||/2)^2. */
+int cg_spherical_dist_fwd(const float* emb, const float* txt, int N, int P, int E, float* dist, void* stream);
+/* gradient of sum_{n,p} gdist[n,p]*dist[n,p] with respect to emb -> demb [N,E]. */
+int cg_spherical_dist_bwd(const float* emb, const float* txt, const float* gdist, int N, int P, int E,
+                          float* demb, void* stream);
+/* Fused form used by the fast cond_fn (sample.py:179-198): loss_out[0] (+)= coef * sum_n sum_p w[p]*dist[n,p],
+ * demb [N,E] = d(that)/d emb, one pass.  w may be NULL (all ones).  loss_out may be NULL. */
+int cg_spherical_loss_fwd_bwd(const float* emb, const float* txt, const float* w, int N, int P, int E, float coef,
+                              float* loss_out, float* demb, void* stream);
+
+/* ------------------------------------------------------------------ cutouts --------------- */
+
+/* flag bits of cg_cut_t.flags */
+#define CG_CUT_GRAY_PRE 1  /* grayscale the source crop before resampling (inner cuts, cutouts.py:102-103) */
+#define CG_CUT_GRAY_POST 2 /* grayscale after resampling (overview variants, cutouts.py:72,76)           */
+#define CG_CUT_HFLIP 4     /* horizontal flip after resampling (overview variants, cutouts.py:74,76)     */
+#define CG_CUT_OVERVIEW 8  /* informational: source is the zero-padded square (cutouts.py:54-64)         */
+
+/* One cutout: the square crop [y0,y0+size) x [x0,x0+size) of the image (coordinates may lie outside
+ * the image: those pixels are zero, cutouts.py:54-62), resampled to cut_size^2 with ResizeRight's
+ * antialiased cubic (cutouts.py:64,105). */
+typedef struct {
+  int32_t y0, x0, size, flags;
+} cg_cut_t;
+
+/* The per-call augmentation parameters of cutouts.py:31-45 (one set for the whole batch) plus the
+ * epilogue (CLIP_NORMALIZE, utils/functional.py:16-18,100). */
+typedef struct {
+  int32_t flip;        /* RandomHorizontalFlip coin */
+  int32_t gray;        /* RandomGrayscale coin */
+  int32_t perm[4];     /* ColorJitter op order: 0 brightness, 1 contrast, 2 saturation, 3 hue */
+  float theta[6];      /* torchvision inverse affine matrix (output -> input), row major 2x3 */
+  float theta_fwd[6];  /* its inverse (input -> output), used by the backward gather */
+  float brightness, contrast, saturation, hue;
+  int32_t augment;     /* 0: skip the whole augmentation chain (base cutouts only) */
+  int32_t normalize;   /* 1: apply (x-mean)/std at the end */
+  float mean[3], stdv[3];
+  uint64_t noise_seed; /* Philox key when `noise` is NULL */
+  uint64_t cut_index0; /* global index of cutout 0 of this call (shards of one record draw the same noise) */
+  float noise_std;     /* 0.01 in the reference (cutouts.py:34,40,42) */
+  int32_t input01;     /* 1: x_in is already in [0,1] (Cutouts.forward, cutouts.py:47); 0: [-1,1] and the
+                          kernel applies denormalize_image_zero_to_one (image_utils.py:40-42) on load */
+} cg_aug_t;
+
+/* output formats of cg_cutouts_fwd / input format of cg_cutouts_bwd */
+#define CG_FMT_F32_NCHW 0   /* [N,3,cs,cs] fp32 -- what make_cutouts returns */
+#define CG_FMT_BF16_PATCH 1 /* [N, g*g, kpad] bf16, k = c*p*p + py*p + px: the im2col rows of CLIP's conv1 */
+
+size_t cg_cutouts_workspace_bytes(int N, int cs, int max_size);
+
+/* make_cutouts, clip_diffusion/cutouts.py:117-134 (+ CLIP_NORMALIZE) as fused kernels.
+ *   x_in [3,H,W] fp32 in [-1,1]; cuts_h/aug_h are HOST structs (copied asynchronously);
+ *   noise: NULL (generated in-kernel, Philox) or 3 stacked tensors [3][N,3,cs,cs] fp32 of N(0,1) draws;
+ *   out: format `fmt`; for CG_FMT_BF16_PATCH, `patch` divides cs and kpad >= 3*patch*patch (pad is zeroed).
+ *   workspace (cg_cutouts_workspace_bytes) keeps what the backward needs until cg_cutouts_bwd. */
+int cg_cutouts_fwd(const float* x_in, int H, int W, const cg_cut_t* cuts_h, int N, int cs, const cg_aug_t* aug_h,
+                   const float* noise, void* out, int fmt, int patch, int kpad, void* workspace, void* stream);
+
+/* Backward of the above: dout (same format as out) -> dx_in [3,H,W] fp32:
+ *   dx_in = (accumulate ? dx_in : 0) + coef * d<dout,out>/d x_in.   Deterministic (gather form, no atomics).
+ *   input01 must equal the forward's aug_h->input01. */
+int cg_cutouts_bwd(const void* dout, int H, int W, int N, int cs, int fmt, int patch, int kpad, float coef,
+                   int accumulate, int input01, float* dx_in, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------ CLIP ViT -------------- */
+/* The OpenAI CLIP VisionTransformer reached through embed_image (utils/functional.py:97-102,
+ * models.py:76-80): building blocks.  Activations are bf16 row-major [M, D]; the residual stream
+ * and its gradient are fp32. */
+
+/* LayerNorm forward (eps 1e-5): y_bf16[M,D] = LN(x_f32[M,D]) * gamma + beta; saves mean/rstd [M]. */
+int cg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int D, int64_t x_row_stride,
+                     void* y_bf16, float* mean, float* rstd, void* stream);
+/* LayerNorm backward (frozen gamma/beta => input gradient only):
+ *   dx[M,D] (+)= LN'(dy_f32[M,D]); optionally writes a bf16 copy of the updated dx. */
+int cg_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                     int M, int D, int64_t x_row_stride, int accumulate, float* dx, void* dx_bf16, void* stream);
+
+/* GEMM epilogues (all: acc[M,N] = A[M,K] . B[N,K]^T, bf16 operands K-major, fp32 accumulation in TMEM) */
+#define CG_EPI_BIAS_BF16 0        /* out_bf16 = acc + bias                                     (QKV)          */
+#define CG_EPI_BIAS_RESID_F32 1   /* resid_f32 += acc + bias                                   (out-proj, c_proj) */
+#define CG_EPI_BIAS_QGELU_BF16 2  /* aux_bf16 = u = acc + bias ; out_bf16 = u*sigmoid(1.702u)  (c_fc)         */
+#define CG_EPI_DQGELU_BF16 3      /* out_bf16 = acc * QuickGELU'(aux_bf16)                     (c_proj dgrad) */
+#define CG_EPI_F32 4              /* out_f32 = acc                                             (dgrad into LN) */
+#define CG_EPI_BF16 5             /* out_bf16 = acc                                            (out-proj dgrad) */
+#define CG_EPI_PATCH_POS_F32 6    /* out_f32[(m/g2)*(g2+1)+1+m%g2, :] = acc + pos[1+m%g2, :]   (conv1 patch embed) */
+
+/* tcgen05/TMEM/TMA GEMM.  A [M,K] bf16 row-major (lda elements), B [N,K] bf16 row-major (ldb); K % 64 == 0,
+ * N % 128 == 0.  out/aux/bias/pos as the epilogue needs (others NULL); ldo = leading dimension of out/aux
+ * in elements; g2 = patches per image for CG_EPI_PATCH_POS_F32. */
+int cg_gemm_bf16_tn(const void* A, const void* B, int M, int N, int K, int64_t lda, int64_t ldb, int epilogue,
+                    const float* bias, void* out, void* aux, int64_t ldo, const float* pos, int g2, void* stream);
+
+/* Fused multi-head attention over packed qkv [Nimg*T, 3*D] bf16 (q | k | v, head h at column h*64), head_dim 64,
+ * softmax scale 1/8.  ctx [Nimg*T, D] bf16, lse [Nimg, heads, T] fp32. */
+int cg_attention_fwd(const void* qkv, int Nimg, int T, int heads, void* ctx, float* lse, void* stream);
+/* dgrad: dctx [Nimg*T, D] bf16 -> dqkv [Nimg*T, 3*D] bf16 (recomputes P from q,k,lse). */
+int cg_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, int Nimg, int T, int heads,
+                     void* dqkv, float* delta_ws, void* stream);
+
+/* Small helpers of the tower. */
+/* x[n*T + 0, :] = cls + pos[0]  (class token rows of the residual stream). */
+int cg_vit_set_cls_rows(const float* cls, const float* pos, int Nimg, int T, int D, float* x, void* stream);
+/* emb[N,E] = y_bf16[N,D] @ proj[D,E] (fp32 accumulate)  and its dgrad dy[N,D] = demb[N,E] @ proj^T. */
+int cg_vit_proj_fwd(const void* y_bf16, const float* proj, int N, int D, int E, float* emb, void* stream);
+int cg_vit_proj_bwd(const float* demb, const float* proj, int N, int D, int E, float* dy, void* stream);
+/* dgrad of the patch embedding + the cutout epilogue layout: dpatch_bf16 [N*g2, kpad] = dx_tok[N,T,D](rows 1..) @ W[D,kpad]
+ * is a plain cg_gemm_bf16_tn with a strided A; no extra entry point. */
+/* fp32 -> bf16 conversion with row remap (drops the class-token row of every image): out[n*g2+j, :] = x[n*T+1+j, :]. */
+int cg_vit_tokens_to_bf16(const float* x, int Nimg, int T, int D, int drop_cls, void* out_bf16, void* stream);
+
+/* ------------------------------------------------------------------ cond_fn tail ---------- */
+/* sample.py:228-238: NaN guard + RMS-normalised clamp, on device (no host sync):
+ *   if any(isnan(g)) out = 0 else { m = sqrt(mean(g^2)); out = sign * g * clamp(m,-thr,thr)/m }.
+ * `scratch` is 2 floats of device memory. */
+int cg_grad_finalize(const float* g, int64_t n, float sign, float thr, float* out, float* scratch, void* stream);
+/* any(isnan(g)) -> flag[0] (1.0f/0.0f), device side. */
+int cg_any_nan(const float* g, int64_t n, float* flag, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPGUIDE_B200_H */

@@ -1,0 +1,133 @@
+"""GPU parity: fused cutout kernels against the CPU oracle (oracle/cutouts.py, itself pinned bit-exactly
+to the reference's Cutouts.forward executed in place -- tests/test_oracle_pins.py).  Same RNG record on
+both sides (noise tensors passed explicitly), so pixels are compared at 1e-5 and the crop parameters are
+the same integers by construction; the drop-in entry point's own record is checked against the
+reference-ordered draw in test_make_cutouts_dropin_record."""
+import pytest
+import torch
+
+from oracle import cutouts as OC
+
+pytestmark = pytest.mark.gpu
+
+PIXEL_TOL = 1e-5  # max abs, fp32
+GRAD_TOL = 1e-4   # relative L2
+
+CASES = [
+    # H, W, cs, n_over, n_inner, power, gray_portion, seed
+    (256, 256, 224, 4, 4, 5, 0.3, 0),
+    (256, 256, 224, 12, 4, 5, 0.3, 1),
+    (512, 768, 224, 2, 6, 5, 0.7, 2),
+    (768, 512, 336, 0, 5, 5, 0.0, 3),
+    (512, 512, 224, 16, 16, 5, 0.3, 4),
+    (256, 320, 224, 3, 0, 5, 0.3, 5),
+    (224, 224, 224, 1, 3, 5, 0.5, 6),   # every crop is an identity resize
+    (512, 512, 224, 0, 1, 1, 0.0, 7),
+    (64, 64, 32, 5, 7, 2, 0.4, 8),
+    (512, 512, 224, 1, 8, 5, 0.3, 9),
+    (512, 512, 224, 3, 8, 5, 0.3, 10),
+    (512, 512, 224, 6, 2, 0.5, 1.0, 11),
+]
+
+
+def _record(case):
+    from clip_diffusion_b200.rng_record import draw_cutout_record
+
+    H, W, cs, no, ni, p, gp, seed = case
+    g = torch.Generator().manual_seed(seed)
+    x = torch.tanh(torch.randn(1, 3, H, W, generator=g)) * 1.1
+    rec = draw_cutout_record(H, W, cs, no, ni, p, gp, generator=g, noise="cpu")
+    return x, rec
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cutouts_forward_backward(case):
+    from clip_diffusion_b200.cutouts import make_cutouts_from_record
+
+    x, rec = _record(case)
+    xr = x.clone().requires_grad_()
+    ref = OC.make_cutouts(xr, rec)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(99))
+    (gref,) = torch.autograd.grad((ref * w).sum(), xr)
+
+    xc = x.cuda().requires_grad_()
+    out = make_cutouts_from_record(xc, rec)
+    (gout,) = torch.autograd.grad((out * w.cuda()).sum(), xc)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    err = (out.cpu() - ref).abs().max().item()
+    assert err <= PIXEL_TOL, "pixel max-abs error %g" % err
+    rel = ((gout.cpu() - gref).norm() / gref.norm()).item()
+    assert rel <= GRAD_TOL, "gradient rel-L2 %g" % rel
+
+
+@pytest.mark.parametrize("case", CASES[:4])
+def test_base_cutouts_only(case):
+    """augment=0: resample + gray/flip variants only (cutouts.py:47-111)."""
+    from clip_diffusion_b200.cutouts import cutouts_forward
+
+    x, rec = _record(case)
+    ref = OC.base_cutouts(x.add(1).div(2), rec)
+    out, _ = cutouts_forward(x.cuda(), rec, augment=False)
+    assert (out.cpu() - ref).abs().max().item() <= PIXEL_TOL
+
+
+def test_normalized_patch_layout_matches_nchw():
+    """CG_FMT_BF16_PATCH (the conv1 im2col layout fed to the ViT) carries the same pixels as NCHW + CLIP_NORMALIZE."""
+    from clip_diffusion_b200 import _lib
+    from clip_diffusion_b200.cutouts import cutouts_forward
+
+    x, rec = _record(CASES[0])
+    ref = OC.clip_normalize(OC.make_cutouts(x, rec))
+    for patch, kpad in [(32, 3072), (16, 768), (14, 640)]:
+        out, _ = cutouts_forward(x.cuda(), rec, fmt=_lib.CG_FMT_BF16_PATCH, patch=patch, kpad=kpad, normalize=True)
+        n, cs = rec.num_cuts, rec.cut_size
+        g = cs // patch
+        o = out.float().cpu()
+        assert o.shape == (n, g * g, kpad)
+        assert o[:, :, 3 * patch * patch:].abs().max().item() == 0 if kpad > 3 * patch * patch else True
+        img = o[:, :, : 3 * patch * patch].reshape(n, g, g, 3, patch, patch).permute(0, 3, 1, 4, 2, 5).reshape(n, 3, cs, cs)
+        assert (img - ref).abs().max().item() <= 2e-2  # bf16 rounding of values up to ~2.6
+
+
+def test_make_cutouts_dropin_record():
+    """The drop-in entry point consumes the global CPU generator in the reference's order: crop sizes,
+    offsets, gray flags and augmentation parameters are the same integers/floats as a reference-ordered draw."""
+    from clip_diffusion_b200.cutouts import Cutouts
+    from clip_diffusion_b200.rng_record import draw_cutout_record
+
+    x = torch.rand(1, 3, 256, 320, device="cuda")
+    torch.manual_seed(1234)
+    m = Cutouts(224, 3, 6, 5, 0.3)
+    out = m(x)
+    after = torch.rand(1).item()
+    torch.manual_seed(1234)
+    rec = draw_cutout_record(256, 320, 224, 3, 6, 5, 0.3, noise="device")
+    assert torch.rand(1).item() == after  # exactly the same number of CPU draws were consumed
+    got = m.last_record
+    assert (got.y0, got.x0, got.size, got.flags) == (rec.y0, rec.x0, rec.size, rec.flags)
+    assert (got.flip, got.angle, got.tx, got.ty, got.gray, got.perm) == (rec.flip, rec.angle, rec.tx, rec.ty, rec.gray, rec.perm)
+    assert (got.brightness, got.contrast, got.saturation, got.hue) == (rec.brightness, rec.contrast, rec.saturation, rec.hue)
+    assert out.shape == (9, 3, 224, 224) and torch.isfinite(out).all()
+    assert 0.0 <= out.min().item() and out.max().item() <= 1.0
+
+
+def test_device_noise_statistics():
+    """In-kernel Philox noise: N(0, 0.01^2) like torch.randn_like(x) * 0.01 (cutouts.py:34,40,42)."""
+    from clip_diffusion_b200.cutouts import cutouts_forward
+    from clip_diffusion_b200.rng_record import draw_cutout_record
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.zeros(1, 3, 256, 256)
+    rec = draw_cutout_record(256, 256, 224, 0, 4, 5, 0.0, generator=g, noise="device")
+    rec.noise_seed = 42
+    # neutral augmentation: only the three noise additions act on a constant image
+    rec.flip, rec.angle, rec.tx, rec.ty, rec.gray = False, 0.0, 0, 0, False
+    rec.perm, rec.brightness, rec.contrast, rec.saturation, rec.hue = [0, 1, 2, 3], 1.0, 1.0, 1.0, 0.0
+    rec.flags = [0] * rec.num_cuts
+    out, _ = cutouts_forward(x.cuda(), rec)
+    d = (out - 0.5).flatten()
+    assert abs(d.mean().item()) < 2e-4
+    assert abs(d.std().item() - 0.01 * 3 ** 0.5) < 3e-4
+    rec2 = rec.slice(1, 3)
+    out2, _ = cutouts_forward(x.cuda(), rec2)
+    assert torch.equal(out2, out[1:3])  # a shard draws the same noise as the full batch

@@ -1,0 +1,81 @@
+"""GPU parity: loss kernels (value + analytic gradient) against the CPU oracle (oracle/losses.py =
+restatement of clip_diffusion/losses.py:10-45, gradients from torch autograd).  Calls go through the
+C ABI (ctypes) via the Python mirror of the reference interface."""
+import pytest
+import torch
+
+from oracle import losses as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_VALUE = 2e-6  # relative, fp32 reductions in a different order
+TOL_GRAD = 1e-5   # relative L2
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 256, 256), (1, 3, 512, 512), (2, 3, 64, 96), (1, 3, 67, 53), (1, 1, 1, 1), (1, 3, 768, 512)])
+@pytest.mark.parametrize("which", ["tv", "range"])
+def test_image_losses(shape, which):
+    from clip_diffusion_b200 import losses as L
+
+    g = torch.Generator().manual_seed(hash(shape) % 1000)
+    x = (torch.tanh(torch.randn(shape, generator=g)) * 1.1).requires_grad_()
+    ofn, mfn = (O.total_variational_loss, L.total_variational_loss) if which == "tv" else (O.rgb_range_loss, L.rgb_range_loss)
+    ref = ofn(x)
+    w = torch.arange(1, shape[0] + 1, dtype=torch.float32)
+    (gref,) = torch.autograd.grad((ref * w).sum(), x)
+    xc = x.detach().cuda().requires_grad_()
+    out = mfn(xc)
+    (gout,) = torch.autograd.grad((out * w.cuda()).sum(), xc)
+    assert out.shape == ref.shape
+    assert torch.allclose(out.cpu(), ref, rtol=TOL_VALUE * 10, atol=1e-9)
+    if gref.norm() > 0:
+        assert _rel(gout.cpu(), gref) < TOL_GRAD
+    else:
+        assert gout.abs().max().item() == 0
+
+
+def test_north_star_aliases():
+    from clip_diffusion_b200 import losses as L
+
+    assert L.tv_loss is L.total_variational_loss and L.range_loss is L.rgb_range_loss
+    assert L.spherical_dist_loss is L.square_spherical_distance_loss
+
+
+@pytest.mark.parametrize("N,P,E", [(16, 1, 512), (64, 1, 768), (5, 3, 64), (1, 1, 8), (32, 2, 1024)])
+def test_spherical(N, P, E):
+    from clip_diffusion_b200 import losses as L
+
+    g = torch.Generator().manual_seed(N * 7 + E)
+    x = torch.randn(N, E, generator=g).requires_grad_()
+    y = torch.randn(P, E, generator=g)
+    ref = O.square_spherical_distance_loss(x.unsqueeze(1), y.unsqueeze(0))
+    w = torch.randn(N, P, generator=g)
+    (gref,) = torch.autograd.grad((ref * w).sum(), x)
+    xc = x.detach().cuda().requires_grad_()
+    out = L.square_spherical_distance_loss(xc.unsqueeze(1), y.cuda().unsqueeze(0))
+    (gout,) = torch.autograd.grad((out * w.cuda()).sum(), xc)
+    assert out.shape == ref.shape
+    assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-6)
+    assert _rel(gout.cpu(), gref) < 1e-5
+
+
+def test_spherical_identical_and_opposite():
+    from clip_diffusion_b200 import losses as L
+
+    x = torch.randn(4, 32)
+    same = L.square_spherical_distance_loss(x.cuda().unsqueeze(1), x[:1].cuda().unsqueeze(0)).cpu()
+    ref = O.square_spherical_distance_loss(x.unsqueeze(1), x[:1].unsqueeze(0))
+    assert torch.allclose(same, ref, atol=1e-6)
+    assert abs(same[0, 0].item()) < 1e-6
+
+
+def test_cpu_tensor_is_refused():
+    from clip_diffusion_b200 import losses as L
+    from clip_diffusion_b200._lib import ClipGuideError
+
+    with pytest.raises(ClipGuideError):
+        L.total_variational_loss(torch.zeros(1, 3, 8, 8))
