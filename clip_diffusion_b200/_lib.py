@@ -104,10 +104,16 @@ def load():
             "clip_diffusion_b200 has no CPU or eager fallback." % LIB_PATH
         )
     lib = C.CDLL(LIB_PATH)
+    missing = []
     for name, (res, args) in _SIGNATURES.items():
-        fn = getattr(lib, name)  # AttributeError if the .so is stale: also loud
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)  # stale build: calling it raises below, loudly
+            continue
         fn.restype = res
         fn.argtypes = args
+    lib._cg_missing = missing
     _lib = lib
     return lib
 
@@ -133,6 +139,8 @@ def call(name, *args):
     """Call an int-returning entry point on the current stream (appended as last argument)."""
     global launch_count
     lib = load()
+    if name in lib._cg_missing:
+        raise ClipGuideError("%s is not exported by %s: rebuild the library (stale build)" % (name, LIB_PATH))
     rc = getattr(lib, name)(*args, stream_ptr())
     launch_count += 1
     check(rc, name)

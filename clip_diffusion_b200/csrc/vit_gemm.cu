@@ -1,0 +1,434 @@
+// bf16 GEMM for the CLIP ViT (QKV / out-proj / MLP / patch-embed and their dgrads) on the 5th-gen tensor
+// cores of sm_100a:  acc[M,N] = A[M,K] . B[N,K]^T,  fp32 accumulation in TMEM, fused epilogues.
+//
+//   * operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) into a 4-stage shared-memory ring;
+//   * one elected thread issues tcgen05.mma (cta_group::1, M=128, N=BN, K=16 per instruction);
+//   * the accumulator lives in TMEM and is double buffered (2 x BN columns), so the epilogue of tile i
+//     overlaps the main loop of tile i+1;
+//   * persistent: one CTA per SM walks the tile list (tile = blockIdx.x + i*gridDim.x), consecutive
+//     tiles share the A row-block so it is reused out of L2;
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (tcgen05.ld ->
+//     registers -> bias / QuickGELU / residual -> global).
+//
+// Weights are frozen (models.py:71), so every GEMM of the backward pass is a dgrad with a pre-transposed
+// weight copy: all calls have both operands K-major and share this one kernel.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 256;
+
+struct GemmArgs {
+  int M, N, K;
+  const float* bias;
+  void* out;
+  void* aux;
+  long long ldo;
+  const float* pos;
+  int g2;
+};
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused (=1).
+// Bits: [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1 (Blackwell), [61,64) layout (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16: D fp32, A/B bf16, both K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float qgelu(float u) { return u / (1.f + __expf(-1.702f * u)); }
+__device__ __forceinline__ float qgelu_grad(float u) {
+  const float s = 1.f / (1.f + __expf(-1.702f * u));
+  return s * (1.f + 1.702f * u * (1.f - s));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// one 32-column chunk of one output row
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, long long row, long long orow, int col, const uint32_t* acc_u) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc_u[j]);
+  if (EPI == CG_EPI_BIAS_BF16 || EPI == CG_EPI_BIAS_RESID_F32 || EPI == CG_EPI_BIAS_QGELU_BF16) {
+    const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  if (EPI == CG_EPI_BIAS_RESID_F32 || EPI == CG_EPI_F32 || EPI == CG_EPI_PATCH_POS_F32) {
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + orow * g.ldo + col);
+    if (EPI == CG_EPI_PATCH_POS_F32) {
+      const float4* p4 = reinterpret_cast<const float4*>(g.pos + (1 + row % g.g2) * (long long)g.N + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 p = __ldg(p4 + j);
+        o4[j] = make_float4(v[4 * j] + p.x, v[4 * j + 1] + p.y, v[4 * j + 2] + p.z, v[4 * j + 3] + p.w);
+      }
+    } else if (EPI == CG_EPI_BIAS_RESID_F32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 p = o4[j];
+        o4[j] = make_float4(v[4 * j] + p.x, v[4 * j + 1] + p.y, v[4 * j + 2] + p.z, v[4 * j + 3] + p.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  } else {
+    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + col);
+    if (EPI == CG_EPI_BIAS_QGELU_BF16) {
+      uint4* a4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.aux) + orow * g.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        a4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                           pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        // the backward differentiates QuickGELU at the bf16-rounded pre-activation it stored
+        v[j] = qgelu(v[j]);
+      }
+    } else if (EPI == CG_EPI_DQGELU_BF16) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.aux) + orow * g.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 a = __ldg(a4 + j);
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+          v[8 * j + 2 * k] *= qgelu_grad(__low2float(p));
+          v[8 * j + 2 * k + 1] *= qgelu_grad(__high2float(p));
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                         pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                       const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
+
+  // 1024-byte alignment for the 128B swizzle
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = g.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(a_dst, &tmA, full_bar(stage), kb * BK, m_blk * BM);
+          tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + stage * STAGE_BYTES, b_addr = a_addr + A_BYTES;
+          const uint64_t adesc = make_smem_desc(a_addr), bdesc = make_smem_desc(b_addr);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot free once these MMAs have read it
+          if (kb == k_blocks - 1) umma_commit(tfull_bar(as));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tfull_bar(as), aphase);
+      tcgen05_fence_after();
+      const long long row = (long long)m_blk * BM + q * 32 + lane;
+      long long orow = row;
+      if (EPI == CG_EPI_PATCH_POS_F32) orow = (row / g.g2) * (g.g2 + 1) + 1 + row % g.g2;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t acc[32];
+        tmem_ld32(t_row + (uint32_t)c, acc);
+        tmem_ld_wait();
+        if (row < g.M) epilogue_chunk<EPI>(g, row, orow, n_blk * BN + c, acc);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long rows, cols, ld;
+  int box_rows;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h ^= std::hash<long long>()(k.rows * 1315423911LL + k.cols * 2654435761LL + k.ld * 97LL + k.box_rows) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+// [rows, cols] bf16 row-major with leading dimension ld; box = 64 columns x box_rows rows, 128B swizzle.
+int make_tensor_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  const MapKey key = {ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { cg_set_error("cuTensorMapEncodeTiled is not available from the driver"); return CG_EARCH; }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { cg_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld); return CG_EINVAL; }
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = CG_NUM_SMS;
+  }
+  return n;
+}
+
+template <int BN, int EPI>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static bool configured = false;
+  if (!configured) {
+    CG_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_tn_kernel<BN, EPI><<<grid, NUM_THREADS, smem, s>>>(ta, tb, g);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+int dispatch(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t s) {
+  switch (epi) {
+    case CG_EPI_BIAS_BF16: return launch<BN, CG_EPI_BIAS_BF16>(ta, tb, g, s);
+    case CG_EPI_BIAS_RESID_F32: return launch<BN, CG_EPI_BIAS_RESID_F32>(ta, tb, g, s);
+    case CG_EPI_BIAS_QGELU_BF16: return launch<BN, CG_EPI_BIAS_QGELU_BF16>(ta, tb, g, s);
+    case CG_EPI_DQGELU_BF16: return launch<BN, CG_EPI_DQGELU_BF16>(ta, tb, g, s);
+    case CG_EPI_F32: return launch<BN, CG_EPI_F32>(ta, tb, g, s);
+    case CG_EPI_BF16: return launch<BN, CG_EPI_BF16>(ta, tb, g, s);
+    case CG_EPI_PATCH_POS_F32: return launch<BN, CG_EPI_PATCH_POS_F32>(ta, tb, g, s);
+  }
+  cg_set_error("cg_gemm_bf16_tn: unknown epilogue %d", epi);
+  return CG_EINVAL;
+}
+
+}  // namespace
+
+extern "C" int cg_gemm_bf16_tn(const void* A, const void* B, int M, int N, int K, int64_t lda, int64_t ldb, int epilogue, const float* bias,
+                               void* out, void* aux, int64_t ldo, const float* pos, int g2, void* stream) {
+  CG_REQUIRE(A && B && out, "cg_gemm_bf16_tn: null operand");
+  CG_REQUIRE(M > 0 && N > 0 && K > 0, "cg_gemm_bf16_tn: bad sizes M=%d N=%d K=%d", M, N, K);
+  CG_REQUIRE(K % BK == 0, "cg_gemm_bf16_tn: K=%d must be a multiple of %d", K, BK);
+  CG_REQUIRE(N % 128 == 0, "cg_gemm_bf16_tn: N=%d must be a multiple of 128", N);
+  CG_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "cg_gemm_bf16_tn: leading dimensions must be >= K and multiples of 8");
+  CG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)out & 15) == 0, "cg_gemm_bf16_tn: pointers must be 16-byte aligned");
+  CG_REQUIRE(ldo % 8 == 0 && ldo >= N, "cg_gemm_bf16_tn: ldo=%lld must be >= N and a multiple of 8", (long long)ldo);
+  const bool needs_bias = epilogue == CG_EPI_BIAS_BF16 || epilogue == CG_EPI_BIAS_RESID_F32 || epilogue == CG_EPI_BIAS_QGELU_BF16;
+  CG_REQUIRE(!needs_bias || bias, "cg_gemm_bf16_tn: epilogue %d needs a bias", epilogue);
+  CG_REQUIRE((epilogue != CG_EPI_BIAS_QGELU_BF16 && epilogue != CG_EPI_DQGELU_BF16) || aux, "cg_gemm_bf16_tn: epilogue %d needs aux", epilogue);
+  CG_REQUIRE(epilogue != CG_EPI_PATCH_POS_F32 || (pos && g2 > 0 && M % g2 == 0), "cg_gemm_bf16_tn: patch epilogue needs pos and g2 | M");
+  const int bn = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb;
+  int rc = make_tensor_map(&ta, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_tensor_map(&tb, B, N, K, ldb, bn);
+  if (rc) return rc;
+  GemmArgs g = {M, N, K, bias, out, aux, (long long)ldo, pos, g2};
+  cudaStream_t s = cg_stream(stream);
+  return bn == 256 ? dispatch<256>(epilogue, ta, tb, g, s) : dispatch<128>(epilogue, ta, tb, g, s);
+}
