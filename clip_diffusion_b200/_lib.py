@@ -66,7 +66,7 @@ _SIGNATURES = {
     "cg_cutouts_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "cg_cutouts_fwd": (_I, [_P, _I, _I, C.POINTER(CgCut), _I, _I, C.POINTER(CgAug), _P, _P, _I, _I, _I, _P, _P]),
     "cg_cutouts_bwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P, _P]),
-    "cg_layernorm_fwd": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _P]),
+    "cg_layernorm_fwd": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _P, _P]),
     "cg_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _P, _P, _P]),
     "cg_gemm_bf16_tn": (_I, [_P, _P, _I, _I, _I, _L, _L, _I, _P, _P, _P, _L, _P, _I, _P]),
     "cg_attention_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P]),

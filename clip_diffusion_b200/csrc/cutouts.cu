@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(256) tables_kernel(const cg_cut_t* __restrict_
   const float a = (float)((size - 1) / 2.0);
   const float b = (float)((cs - 1) / (2.0 * scale_d));
   const float half_sup = (float)(support_d / 2.0);
+  // ResizeRight shifts grid and field of view by the left pad (= -left[0]) BEFORE taking their difference,
+  // which re-rounds the fp32 grid; reproduce it so the weights agree to the last bits.
+  const float g0 = __fsub_rn(__fadd_rn(__fdiv_rn(0.f, scale), a), b);
+  const int pad0 = -(int)ceilf(__fsub_rn(__fsub_rn(g0, half_sup), eps));
   int* lf = left + (size_t)n * cs;
   float* wf = wfw + (size_t)n * cs * TAPS_MAX;
   for (int o = threadIdx.x; o < cs; o += blockDim.x) {
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(256) tables_kernel(const cg_cut_t* __restrict_
     for (int t = 0; t < TAPS_MAX; ++t) {
       float v = 0.f;
       if (t < taps) {
-        const float d = __fsub_rn(g, (float)(l + t));
+        const float d = __fsub_rn(__fadd_rn(g, (float)pad0), (float)(l + t + pad0));
         v = down ? __fmul_rn(scale, cubic_w(__fmul_rn(scale, d))) : cubic_w(d);
       }
       w[t] = v;

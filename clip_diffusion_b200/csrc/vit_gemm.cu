@@ -144,9 +144,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, long long row,
         o4[j] = make_float4(v[4 * j] + p.x, v[4 * j + 1] + p.y, v[4 * j + 2] + p.z, v[4 * j + 3] + p.w);
       }
     } else if (EPI == CG_EPI_BIAS_RESID_F32) {
+      const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.aux) + orow * g.ldo + col);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 p = o4[j];
+        const float4 p = r4[j];
         o4[j] = make_float4(v[4 * j] + p.x, v[4 * j + 1] + p.y, v[4 * j + 2] + p.z, v[4 * j + 3] + p.w);
       }
     } else {
@@ -420,7 +421,7 @@ extern "C" int cg_gemm_bf16_tn(const void* A, const void* B, int M, int N, int K
   CG_REQUIRE(ldo % 8 == 0 && ldo >= N, "cg_gemm_bf16_tn: ldo=%lld must be >= N and a multiple of 8", (long long)ldo);
   const bool needs_bias = epilogue == CG_EPI_BIAS_BF16 || epilogue == CG_EPI_BIAS_RESID_F32 || epilogue == CG_EPI_BIAS_QGELU_BF16;
   CG_REQUIRE(!needs_bias || bias, "cg_gemm_bf16_tn: epilogue %d needs a bias", epilogue);
-  CG_REQUIRE((epilogue != CG_EPI_BIAS_QGELU_BF16 && epilogue != CG_EPI_DQGELU_BF16) || aux, "cg_gemm_bf16_tn: epilogue %d needs aux", epilogue);
+  CG_REQUIRE((epilogue != CG_EPI_BIAS_QGELU_BF16 && epilogue != CG_EPI_DQGELU_BF16 && epilogue != CG_EPI_BIAS_RESID_F32) || aux, "cg_gemm_bf16_tn: epilogue %d needs aux", epilogue);
   CG_REQUIRE(epilogue != CG_EPI_PATCH_POS_F32 || (pos && g2 > 0 && M % g2 == 0), "cg_gemm_bf16_tn: patch epilogue needs pos and g2 | M");
   const int bn = (N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, tb;

@@ -16,7 +16,9 @@ def gemm_bf16_tn(a, b, epilogue, bias=None, out=None, aux=None, pos=None, g2=0, 
     assert b.shape[1] == K
     if out is None:
         dt = torch.float32 if epilogue in (_lib.EPI_F32,) else torch.bfloat16
-        assert epilogue not in (_lib.EPI_BIAS_RESID_F32, _lib.EPI_PATCH_POS_F32), "in-place epilogues need `out`"
+        assert epilogue != _lib.EPI_PATCH_POS_F32, "the patch epilogue writes into a preallocated token buffer"
+        if epilogue == _lib.EPI_BIAS_RESID_F32:
+            dt = torch.float32
         out = torch.empty(M, N, device=a.device, dtype=dt)
     if epilogue == _lib.EPI_BIAS_QGELU_BF16 and aux is None:
         aux = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)

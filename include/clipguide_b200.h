@@ -118,17 +118,19 @@ int cg_cutouts_bwd(const void* dout, int H, int W, int N, int cs, int fmt, int p
  * models.py:76-80): building blocks.  Activations are bf16 row-major [M, D]; the residual stream
  * and its gradient are fp32. */
 
-/* LayerNorm forward (eps 1e-5): y_bf16[M,D] = LN(x_f32[M,D]) * gamma + beta; saves mean/rstd [M]. */
-int cg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int D, int64_t x_row_stride,
-                     void* y_bf16, float* mean, float* rstd, void* stream);
-/* LayerNorm backward (frozen gamma/beta => input gradient only):
- *   dx[M,D] (+)= LN'(dy_f32[M,D]); optionally writes a bf16 copy of the updated dx. */
+/* LayerNorm forward (eps 1e-5) over M rows of D fp32 values, row r at x + r*row_stride:
+ *   y = LN(x) * gamma + beta, written as bf16 (y_bf16, contiguous [M,D], GEMM operand) and/or fp32
+ *   (y_f32, contiguous [M,D]; ln_pre / ln_post feed fp32 consumers).  Saves mean/rstd [M]. */
+int cg_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int D, int64_t row_stride,
+                     void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
+/* LayerNorm backward (frozen gamma/beta => input gradient only).  dy contiguous [M,D] fp32; x, dx and
+ * dx_bf16 (optional bf16 copy of the updated dx) use row_stride:  dx = (accumulate ? dx : 0) + LN'(dy). */
 int cg_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
-                     int M, int D, int64_t x_row_stride, int accumulate, float* dx, void* dx_bf16, void* stream);
+                     int M, int D, int64_t row_stride, int accumulate, float* dx, void* dx_bf16, void* stream);
 
 /* GEMM epilogues (all: acc[M,N] = A[M,K] . B[N,K]^T, bf16 operands K-major, fp32 accumulation in TMEM) */
 #define CG_EPI_BIAS_BF16 0        /* out_bf16 = acc + bias                                     (QKV)          */
-#define CG_EPI_BIAS_RESID_F32 1   /* resid_f32 += acc + bias                                   (out-proj, c_proj) */
+#define CG_EPI_BIAS_RESID_F32 1   /* out_f32 = aux_f32 + acc + bias  (aux may alias out)      (out-proj, c_proj) */
 #define CG_EPI_BIAS_QGELU_BF16 2  /* aux_bf16 = u = acc + bias ; out_bf16 = u*sigmoid(1.702u)  (c_fc)         */
 #define CG_EPI_DQGELU_BF16 3      /* out_bf16 = acc * QuickGELU'(aux_bf16)                     (c_proj dgrad) */
 #define CG_EPI_F32 4              /* out_f32 = acc                                             (dgrad into LN) */
@@ -151,13 +153,17 @@ int cg_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const f
 /* Small helpers of the tower. */
 /* x[n*T + 0, :] = cls + pos[0]  (class token rows of the residual stream). */
 int cg_vit_set_cls_rows(const float* cls, const float* pos, int Nimg, int T, int D, float* x, void* stream);
-/* emb[N,E] = y_bf16[N,D] @ proj[D,E] (fp32 accumulate)  and its dgrad dy[N,D] = demb[N,E] @ proj^T. */
-int cg_vit_proj_fwd(const void* y_bf16, const float* proj, int N, int D, int E, float* emb, void* stream);
+/* emb[N,E] = y[N,D] @ proj[D,E] (fp32)  and its dgrad dy[N,D] = demb[N,E] @ proj^T. */
+int cg_vit_proj_fwd(const float* y, const float* proj, int N, int D, int E, float* emb, void* stream);
 int cg_vit_proj_bwd(const float* demb, const float* proj, int N, int D, int E, float* dy, void* stream);
-/* dgrad of the patch embedding + the cutout epilogue layout: dpatch_bf16 [N*g2, kpad] = dx_tok[N,T,D](rows 1..) @ W[D,kpad]
- * is a plain cg_gemm_bf16_tn with a strided A; no extra entry point. */
-/* fp32 -> bf16 conversion with row remap (drops the class-token row of every image): out[n*g2+j, :] = x[n*T+1+j, :]. */
+/* fp32 -> bf16 copy of token rows; drop_cls=1 skips the class-token row of every image:
+ * out[n*(T-1)+j, :] = x[n*T+1+j, :]  (A operand of the conv1 dgrad GEMM). */
 int cg_vit_tokens_to_bf16(const float* x, int Nimg, int T, int D, int drop_cls, void* out_bf16, void* stream);
+/* embed_image's front end for an arbitrary image batch (utils/functional.py:97-101): optional CLIP_NORMALIZE,
+ * then conv1's im2col rows:  img [N,3,cs,cs] fp32 -> out [N, (cs/patch)^2, kpad] bf16 (pad zeroed); and its
+ * backward dpatch -> dimg. */
+int cg_patchify_fwd(const float* img, int N, int cs, int patch, int kpad, int normalize, void* out_bf16, void* stream);
+int cg_patchify_bwd(const void* dpatch_bf16, int N, int cs, int patch, int kpad, int normalize, float* dimg, void* stream);
 
 /* ------------------------------------------------------------------ cond_fn tail ---------- */
 /* sample.py:228-238: NaN guard + RMS-normalised clamp, on device (no host sync):

@@ -11,7 +11,13 @@ from oracle import cutouts as OC
 pytestmark = pytest.mark.gpu
 
 PIXEL_TOL = 1e-5  # max abs, fp32
-GRAD_TOL = 1e-4   # relative L2
+GRAD_TOL = 5e-3   # relative L2 over the whole gradient; see GRAD_TOL_TRIMMED
+# The augmentation chain is only piecewise differentiable (clamp masks in _blend, max/min and sextant
+# selection in the HSV round trip).  A pixel sitting within float rounding of such a boundary may take the other
+# (equally valid) sub-gradient; one flipped output pixel perturbs a ~10x10 source footprint.  Measured: all but
+# 0-2 cutouts of 32 agree to 3e-7; a flip gives ~5e-4 overall.  So: a loose bound on everything (north_star's is
+# 1e-2) and a tight bound once the 0.1% worst source pixels are trimmed.
+GRAD_TOL_TRIMMED = 2e-5
 
 CASES = [
     # H, W, cs, n_over, n_inner, power, gray_portion, seed
@@ -56,8 +62,12 @@ def test_cutouts_forward_backward(case):
     assert out.shape == ref.shape and out.dtype == torch.float32
     err = (out.cpu() - ref).abs().max().item()
     assert err <= PIXEL_TOL, "pixel max-abs error %g" % err
-    rel = ((gout.cpu() - gref).norm() / gref.norm()).item()
+    diff = (gout.cpu() - gref).flatten()
+    rel = (diff.norm() / gref.norm()).item()
     assert rel <= GRAD_TOL, "gradient rel-L2 %g" % rel
+    keep = diff.abs().argsort()[: int(diff.numel() * 0.999)]
+    rel_trim = (diff[keep].norm() / gref.norm()).item()
+    assert rel_trim <= GRAD_TOL_TRIMMED, "trimmed gradient rel-L2 %g" % rel_trim
 
 
 @pytest.mark.parametrize("case", CASES[:4])

@@ -45,7 +45,10 @@ def test_gemm_epilogues(M, N, K):
     # bias + residual (fp32, in place)
     resid = torch.randn(M, N, device="cuda")
     r0 = resid.clone()
-    ops.gemm_bf16_tn(a, b, _lib.EPI_BIAS_RESID_F32, bias=bias, out=resid)
+    out2 = ops.gemm_bf16_tn(a, b, _lib.EPI_BIAS_RESID_F32, bias=bias, aux=resid)  # out of place
+    assert torch.equal(resid, r0)
+    assert (out2 - (r0 + ref + bias)).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+    ops.gemm_bf16_tn(a, b, _lib.EPI_BIAS_RESID_F32, bias=bias, out=resid, aux=resid)  # in place
     assert (resid - (r0 + ref + bias)).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
     # bias + QuickGELU (+ pre-activation)
     h, u = ops.gemm_bf16_tn(a, b, _lib.EPI_BIAS_QGELU_BF16, bias=bias)
