@@ -77,7 +77,7 @@ _SIGNATURES = {
     "cg_vit_tokens_to_bf16": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "cg_patchify_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "cg_patchify_bwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
-    "cg_grad_finalize": (_I, [_P, _L, _F, _F, _P, _P, _P]),
+    "cg_grad_finalize": (_I, [_P, _L, _F, _F, _P, _P, _P, _P]),
     "cg_any_nan": (_I, [_P, _L, _P, _P]),
 }
 

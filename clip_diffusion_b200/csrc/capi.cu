@@ -47,8 +47,9 @@ __global__ void __launch_bounds__(256) sumsq_nan_kernel(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ g, int64_t n, float sign, float thr,
-                                                       const float* __restrict__ scratch, float* __restrict__ out) {
-  const bool bad = scratch[1] > 0.f;
+                                                       const float* __restrict__ scratch, const float* __restrict__ bad_flag,
+                                                       float* __restrict__ out) {
+  const bool bad = bad_flag ? (bad_flag[0] != 0.f) : (scratch[1] > 0.f);
   const float mag = sqrtf(scratch[0] / (float)n);
   // grad * clamp(mag, -thr, thr) / mag   (sample.py:236-238); mag == 0 gives NaN there as well (0/0)
   const float k = sign * fminf(fmaxf(mag, -thr), thr) / mag;
@@ -66,13 +67,14 @@ static int blocks_for(int64_t n) {
   return (int)(b < 1 ? 1 : b);
 }
 
-extern "C" int cg_grad_finalize(const float* g, int64_t n, float sign, float thr, float* out, float* scratch, void* stream) {
+extern "C" int cg_grad_finalize(const float* g, int64_t n, float sign, float thr, const float* bad_flag, float* out, float* scratch,
+                                void* stream) {
   CG_REQUIRE(g && out && scratch && n > 0, "cg_grad_finalize: bad arguments");
   cudaStream_t s = cg_stream(stream);
   CG_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(float), s));
   sumsq_nan_kernel<<<blocks_for(n), 256, 0, s>>>(g, n, scratch);
   CG_LAUNCH_CHECK();
-  finalize_kernel<<<blocks_for(n), 256, 0, s>>>(g, n, sign, thr, scratch, out);
+  finalize_kernel<<<blocks_for(n), 256, 0, s>>>(g, n, sign, thr, scratch, bad_flag, out);
   CG_LAUNCH_CHECK();
   return 0;
 }

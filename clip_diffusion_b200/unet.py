@@ -1,0 +1,171 @@
+"""Stock-PyTorch ADM UNet (the guided-diffusion epsilon model) -- the REPLICATED part of a guidance step.
+
+north_star keeps "the guided-diffusion UNet epsilon forward" replicated and in stock PyTorch; it is needed here
+only as the workload around the CLIP-guidance kernels (clip_diffusion/models.py:87-131 builds it from the
+un-vendored crowsonkb/guided-diffusion; SURVEY.md App. A.3 restates the architecture).  Nothing in this file is a
+kernel target: convolutions, GroupNorm and attention are torch / cuDNN library calls.
+
+512 config (models.py:95-116): model_channels 256, 2 res blocks, head_channels 64, attention at 32/16/8,
+channel_mult (0.5,1,1,2,2,4,4), resblock_updown, scale-shift norm, learn_sigma (6 output channels), fp16 trunk.
+"""
+import math
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+
+class GroupNorm32(nn.GroupNorm):
+    def forward(self, x):
+        return super().forward(x.float()).type(x.dtype)
+
+
+def timestep_embedding(timesteps, dim, max_period=10000):
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=timesteps.device) / half)
+    args = timesteps[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+class Resample(nn.Module):
+    def __init__(self, up):
+        super().__init__()
+        self.up = up
+
+    def forward(self, x):
+        return F.interpolate(x, scale_factor=2, mode="nearest") if self.up else F.avg_pool2d(x, 2)
+
+
+class ResBlock(nn.Module):
+    def __init__(self, channels, emb_channels, out_channels, up=False, down=False):
+        super().__init__()
+        self.out_channels = out_channels
+        self.in_norm = GroupNorm32(32, channels)
+        self.in_conv = nn.Conv2d(channels, out_channels, 3, padding=1)
+        self.resample = Resample(up) if (up or down) else None
+        self.emb = nn.Linear(emb_channels, 2 * out_channels)  # scale-shift norm
+        self.out_norm = GroupNorm32(32, out_channels)
+        self.out_conv = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+        self.skip = nn.Identity() if out_channels == channels else nn.Conv2d(channels, out_channels, 1)
+
+    def forward(self, x, emb):
+        h = F.silu(self.in_norm(x))
+        if self.resample is not None:
+            h = self.resample(h)
+            x = self.resample(x)
+        h = self.in_conv(h)
+        scale, shift = self.emb(F.silu(emb)).type(h.dtype)[:, :, None, None].chunk(2, dim=1)
+        h = self.out_norm(h) * (1 + scale) + shift
+        h = self.out_conv(F.silu(h))
+        return self.skip(x) + h
+
+
+class AttentionBlock(nn.Module):
+    def __init__(self, channels, head_channels):
+        super().__init__()
+        self.heads = channels // head_channels
+        self.norm = GroupNorm32(32, channels)
+        self.qkv = nn.Conv1d(channels, channels * 3, 1)
+        self.proj = nn.Conv1d(channels, channels, 1)
+
+    def forward(self, x):
+        b, c, hh, ww = x.shape
+        xf = x.reshape(b, c, -1)
+        qkv = self.qkv(self.norm(xf))  # [b, 3c, t], legacy order: heads x (q|k|v) x head_dim
+        t = qkv.shape[-1]
+        q, k, v = qkv.reshape(b * self.heads, 3, c // self.heads, t).unbind(1)
+        a = F.scaled_dot_product_attention(q.transpose(1, 2).unsqueeze(0), k.transpose(1, 2).unsqueeze(0), v.transpose(1, 2).unsqueeze(0))
+        a = a.squeeze(0).transpose(1, 2).reshape(b, c, t)
+        return (xf + self.proj(a)).reshape(b, c, hh, ww)
+
+
+class _Seq(nn.Module):
+    """A list of layers where ResBlocks take the timestep embedding."""
+
+    def __init__(self, *layers):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+
+    def forward(self, x, emb):
+        for layer in self.layers:
+            x = layer(x, emb) if isinstance(layer, ResBlock) else layer(x)
+        return x
+
+
+UNET_CONFIGS = {
+    # image size: (model_channels, channel_mult, attention downsample rates)
+    512: (256, (0.5, 1, 1, 2, 2, 4, 4), (16, 32, 64)),
+    256: (256, (1, 1, 2, 2, 4, 4), (8, 16, 32)),
+    # small variants for tests / CPU baselines
+    64: (64, (1, 2, 2), (2, 4)),
+    32: (32, (1, 2), (2,)),
+}
+
+
+class UNetModel(nn.Module):
+    def __init__(self, image_size=512, num_res_blocks=2, head_channels=64, learn_sigma=True, use_fp16=True, config=None):
+        super().__init__()
+        mc, mult, attn_ds = config if config is not None else UNET_CONFIGS[image_size]
+        self.model_channels = mc
+        self.dtype = torch.float16 if use_fp16 else torch.float32
+        emb_ch = mc * 4
+        self.time_embed = nn.Sequential(nn.Linear(mc, emb_ch), nn.SiLU(), nn.Linear(emb_ch, emb_ch))
+        ch = in_ch = int(mult[0] * mc)
+        hc = min(head_channels, in_ch)
+        self.input_blocks = nn.ModuleList([_Seq(nn.Conv2d(3, ch, 3, padding=1))])
+        chans = [ch]
+        ds = 1
+        for level, m in enumerate(mult):
+            for _ in range(num_res_blocks):
+                layers = [ResBlock(ch, emb_ch, int(m * mc))]
+                ch = int(m * mc)
+                if ds in attn_ds:
+                    layers.append(AttentionBlock(ch, hc))
+                self.input_blocks.append(_Seq(*layers))
+                chans.append(ch)
+            if level != len(mult) - 1:
+                self.input_blocks.append(_Seq(ResBlock(ch, emb_ch, ch, down=True)))
+                chans.append(ch)
+                ds *= 2
+        self.middle_block = _Seq(ResBlock(ch, emb_ch, ch), AttentionBlock(ch, hc), ResBlock(ch, emb_ch, ch))
+        self.output_blocks = nn.ModuleList()
+        for level, m in list(enumerate(mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [ResBlock(ch + chans.pop(), emb_ch, int(m * mc))]
+                ch = int(m * mc)
+                if ds in attn_ds:
+                    layers.append(AttentionBlock(ch, hc))
+                if level and i == num_res_blocks:
+                    layers.append(ResBlock(ch, emb_ch, ch, up=True))
+                    ds //= 2
+                self.output_blocks.append(_Seq(*layers))
+        self.out_norm = GroupNorm32(32, ch)
+        self.out_conv = nn.Conv2d(in_ch, 6 if learn_sigma else 3, 3, padding=1)
+        if use_fp16:
+            for part in (self.input_blocks, self.middle_block, self.output_blocks):
+                for mod in part.modules():
+                    if isinstance(mod, (nn.Conv1d, nn.Conv2d, nn.Linear)):
+                        mod.half()
+
+    def forward(self, x, timesteps, y=None):
+        emb = self.time_embed(timestep_embedding(timesteps, self.model_channels))
+        h = x.type(self.dtype)
+        hs = []
+        for blk in self.input_blocks:
+            h = blk(h, emb)
+            hs.append(h)
+        h = self.middle_block(h, emb)
+        for blk in self.output_blocks:
+            h = blk(torch.cat([h, hs.pop()], dim=1), emb)
+        h = h.type(x.dtype)
+        return self.out_conv(F.silu(self.out_norm(h)))
+
+
+def create_unet(image_size=512, seed=2, device="cuda", use_fp16=True, config=None):
+    """Random-init UNet (no checkpoints offline).  guided-diffusion zero-initialises the last conv of every ResBlock,
+    the attention projections and the output conv; with random weights that would make epsilon identically 0, so
+    they keep PyTorch's default init."""
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)
+        model = UNetModel(image_size, use_fp16=use_fp16, config=config)
+    return model.to(device).eval().requires_grad_(False)

@@ -167,10 +167,12 @@ int cg_patchify_bwd(const void* dpatch_bf16, int N, int cs, int patch, int kpad,
 
 /* ------------------------------------------------------------------ cond_fn tail ---------- */
 /* sample.py:228-238: NaN guard + RMS-normalised clamp, on device (no host sync):
- *   if any(isnan(g)) out = 0 else { m = sqrt(mean(g^2)); out = sign * g * clamp(m,-thr,thr)/m }.
- * `scratch` is 2 floats of device memory. */
-int cg_grad_finalize(const float* g, int64_t n, float sign, float thr, float* out, float* scratch, void* stream);
-/* any(isnan(g)) -> flag[0] (1.0f/0.0f), device side. */
+ *   if (bad) out = 0 else { m = sqrt(mean(g^2)); out = sign * g * clamp(m,-thr,thr)/m }
+ * where bad = bad_flag[0] != 0 when bad_flag is given (the reference tests the PRE-VJP gradient, sample.py:228,
+ * see cg_any_nan) and any(isnan(g)) otherwise.  `scratch` is 2 floats of device memory. */
+int cg_grad_finalize(const float* g, int64_t n, float sign, float thr, const float* bad_flag, float* out, float* scratch,
+                     void* stream);
+/* any(isnan(g)) -> flag[0] (1.0f/0.0f), device side; flag must have room for 2 floats. */
 int cg_any_nan(const float* g, int64_t n, float* flag, void* stream);
 
 #ifdef __cplusplus

@@ -29,16 +29,16 @@ def test_layernorm_fwd_bwd(M, D, stride):
     dy = torch.randn(M, D, generator=g)
     (gref,) = torch.autograd.grad((ref * dy).sum(), x)
     P = _lib.ptr
-    xb = buf.cuda()
+    xb, gc, bc, dyc = buf.cuda(), gamma.cuda(), beta.cuda(), dy.cuda()  # keep device copies alive across the calls
     yb = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
     yf = torch.empty(M, D, device="cuda")
     mean = torch.empty(M, device="cuda"); rstd = torch.empty(M, device="cuda")
-    _lib.call("cg_layernorm_fwd", P(xb), P(gamma.cuda()), P(beta.cuda()), M, D, stride, P(yb), P(yf), P(mean), P(rstd))
+    _lib.call("cg_layernorm_fwd", P(xb), P(gc), P(bc), M, D, stride, P(yb), P(yf), P(mean), P(rstd))
     assert (yf.cpu() - ref.detach()).abs().max().item() < 2e-5
     assert (yb.float().cpu() - ref.detach()).abs().max().item() < 3e-2
     dx = torch.full((M, stride), 3.0, device="cuda")
     dxb = torch.zeros(M, stride, device="cuda", dtype=torch.bfloat16)
-    _lib.call("cg_layernorm_bwd", P(dy.cuda()), P(xb), P(gamma.cuda()), P(mean), P(rstd), M, D, stride, 1, P(dx), P(dxb))
+    _lib.call("cg_layernorm_bwd", P(dyc), P(xb), P(gc), P(mean), P(rstd), M, D, stride, 1, P(dx), P(dxb))
     assert ((dx[:, :D].cpu() - 3.0) - gref).abs().max().item() < 5e-5 * max(1.0, gref.abs().max().item())
     assert (dxb[:, :D].float().cpu() - (gref + 3.0)).abs().max().item() < 5e-2 * max(1.0, gref.abs().max().item())
     if stride > D:
