@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128) sph_bwd_kernel(const float* __restrict__ 
     const float r = sqrtf(r2);
     const float g = gdist ? gdist[(int64_t)n * P + p] : coef * (w ? w[p] : 1.f);
     lsum += g * sph_from_r(r);
-    if (r > 0.f) {
+    if (r != 0.f) {  // NaN must propagate (the reference's NaN guard, sample.py:228, relies on it)
       const float k = g * sph_dr_over_r(r) * ix;
       for (int e = lane; e < E; e += 32) {
         const float xh = x[e] * ix;
