@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Guidance-step benchmark (contract in the task statement; numbers explained in DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|target|c3|c1]
+
+A "step" is ONE full CLIP-guided DDIM sampling step on synthetic inputs: the sampler's no-grad UNet forward, the
+guidance function (UNet forward with grad -> fused cutouts -> CLIP ViT fwd -> spherical loss+grad -> ViT dgrad ->
+cutout backward -> TV -> all-reduce -> UNet VJP -> RMS clamp) and the DDIM update.  Default workload = BASELINE.json
+configs[1]: 512x512 uncond guided-diffusion UNet (fp16, random init) + ViT-B/16, 16 overview + 16 inner cutouts,
+DDIM-250 schedule.  For N > 1 the cutout batch is sharded across ranks (one NCCL all-reduce of the [3,512,512] fp32
+image gradient per step, UNet replicated) => strong scaling.
+
+--impl reference times the CPU restatement of the reference path (oracle/, fp32, all host threads) on the same
+workload; see cpu_baseline in the JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (image size, clip models, overview cuts, inner cuts, cutout batches, ddim steps, description)
+    "c1": (256, ("ViT-B/32",), 12, 4, 1, 250, "256x256 UNet(256 cfg) + ViT-B/32, 12+4 cutouts"),
+    "c2": (512, ("ViT-B/16",), 16, 16, 1, 250, "512x512 uncond guided-diffusion UNet + ViT-B/16, 16 overview + 16 inner cutouts, DDIM-250"),
+    "c3": (512, ("ViT-B/32", "ViT-B/16", "ViT-L/14"), 32, 32, 1, 250, "512x512 UNet + ViT-B/32+B/16+L/14 ensemble, 64 cutouts per model, tv+range"),
+    "target": (512, ("ViT-L/14",), 32, 32, 1, 250, "512x512 UNet + ViT-L/14, 64 cutouts (north_star target)"),
+    "clip-only": (512, ("ViT-L/14",), 32, 32, 1, 250, "ViT-L/14, 64 cutouts, guidance gradient only (no UNet)"),
+}
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=8)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-budget-s", type=float, default=240.0)
+    return p.parse_args()
+
+
+class Cfg:
+    """Config of the benchmarked step (read at call time by the guidance function, like clip_diffusion.config.Config)."""
+    grad_threshold = 0.05
+    clip_guidance_scale = 8000
+    denoise_scale = 10000
+    aesthetic_scale = 0
+
+
+def make_cfg(n_over, n_inner, batches):
+    class C(Cfg):
+        num_cutout_batches = batches
+        num_overview_cuts_schedule = (n_over,) * 1000
+        num_inner_cuts_schedule = (n_inner,) * 1000
+        inner_cut_size_power_schedule = (5,) * 1000
+        cut_gray_portion_schedule = (0.3,) * 1000
+    return C
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def summary(self, t0, t1):
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in rows)
+        reasons = [n for i, n in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap"))
+                   if any(r[i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_cpu_reference(wl, seed=0):
+    """The CPU restatement of the reference path (oracle/): same workload, fp32, torch CPU ops."""
+    from clip_diffusion_b200.diffusion import SpacedDiffusion  # sampler host logic (numpy + torch ops), not a kernel
+    from clip_diffusion_b200.models import random_clip_state_dict
+    from clip_diffusion_b200.rng_record import draw_cutout_record
+    from clip_diffusion_b200.unet import create_unet
+    from oracle.clip_vit import OracleCLIP
+    from oracle.cond_fn import make_conditon_function
+
+    size, names, n_over, n_inner, batches, ddim, _ = WORKLOADS[wl]
+    cfg = make_cfg(n_over, n_inner, batches)
+    unet = create_unet(size if size in (256, 512) else 512, seed=2, device="cpu", use_fp16=False)
+    diffusion = SpacedDiffusion(steps=ddim)
+    g = torch.Generator().manual_seed(seed)
+    clip, text = {}, {}
+    for i, name in enumerate(names):
+        clip[name] = OracleCLIP(name, state_dict=random_clip_state_dict(name, seed=1 + i))
+        text[name] = {"embeddings": torch.randn(1, clip[name].visual.output_dim, generator=g), "weights": torch.tensor(1.0)}
+    state = {"ct": ddim - 1}
+
+    def record_source(name, b, H, W, cs, no, ni, p, gp):
+        return draw_cutout_record(H, W, cs, no, ni, p, gp, noise="cpu")
+
+    cond_fn = make_conditon_function(diffusion, unet, clip, text, lambda: state["ct"], cfg, record_source)
+    x = torch.randn(1, 3, size, size, generator=g)
+
+    def step(x, i):
+        state["ct"] = i
+        t = torch.full((1,), i, dtype=torch.long)
+        return diffusion.ddim_sample(unet, x, t, clip_denoised=False, cond_fn=cond_fn, model_kwargs={})["sample"]
+
+    return step, x, ddim, (n_over + n_inner) * batches * len(names)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    wl = args.workload
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1234)
+    step, x, ddim, cuts = build_cpu_reference(wl)
+    t0 = time.time()
+    i = ddim - 1
+    x = step(x, i)  # warm-up (also sizes the timed part)
+    t_first = time.time() - t0
+    k = max(1, min(args.steps, int((args.cpu_budget_s - t_first) / max(t_first, 1e-3))))
+    t0 = time.time()
+    for j in range(k):
+        i -= 1
+        x = step(x, i)
+    dt = (time.time() - t0) / k
+    val = 1.0 / dt
+    sample = "%d full guidance step(s) after 1 warm-up step (requested %d/%d; bounded to %.0f s of CPU time)" % (k, args.steps, args.warmup, args.cpu_budget_s)
+    line = {
+        "impl": "reference", "metric": "CLIP-guided DDIM steps/s @%dx%d" % (WORKLOADS[wl][0], WORKLOADS[wl][0]), "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": k,
+        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[wl][6], "cutouts_per_step": cuts},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cutouts_per_s": cuts * val,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    from clip_diffusion_b200 import _lib, vit_ops
+    from clip_diffusion_b200.diffusion import SpacedDiffusion
+    from clip_diffusion_b200.models import load_clip_models
+    from clip_diffusion_b200.sample import GuidanceStep
+    from clip_diffusion_b200.unet import create_unet
+    from clip_diffusion_b200.utils.functional import set_seed
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.check(_lib.load().cg_check_device(), "cg_check_device")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    size, names, n_over, n_inner, batches, ddim, desc = WORKLOADS[args.workload]
+    cfg = make_cfg(n_over, n_inner, batches)
+    set_seed(1234)
+    clip_only = args.workload == "clip-only"
+    unet = None if clip_only else create_unet(size if size in (256, 512) else 512, seed=2, device=dev, use_fp16=True)
+    diffusion = SpacedDiffusion(steps=ddim)
+    clip_models = load_clip_models(names, dev)
+    g = torch.Generator().manual_seed(0)
+    text = {n: {"embeddings": torch.randn(1, m.visual.output_dim, generator=g).to(dev), "weights": torch.tensor(1.0, device=dev)} for n, m in clip_models.items()}
+    guidance = GuidanceStep(diffusion, unet, clip_models, text, config=cfg, rank=rank, world_size=world,
+                            range_scale=150.0 if args.workload == "c3" else 0.0)
+    cuts_per_step = (n_over + n_inner) * batches * len(names)
+    x_host = torch.randn(1, 3, size, size, generator=g).pin_memory()
+    out_host = torch.empty(2, 3, size, size).pin_memory()
+    x_dev = x_host.to(dev)
+    x_in_fixed = torch.tanh(x_dev).contiguous()
+
+    def step(x, i):
+        if clip_only:
+            gbuf = torch.zeros(3, size, size, device=dev)
+            guidance.clip_guidance_grad(x_in_fixed, 1000 - (int(diffusion.timestep_map[i]) + 1), gbuf)
+            if world > 1:
+                dist.all_reduce(gbuf)
+            return {"sample": x, "pred_xstart": gbuf.unsqueeze(0)}
+        guidance.current_timestep = i
+        t = torch.full((1,), i, device=dev, dtype=torch.long)
+        return diffusion.ddim_sample(unet, x, t, clip_denoised=False, cond_fn=guidance.cond_fn, model_kwargs={})
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def tmax(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    W, K = max(args.warmup, 3), args.steps
+    i = ddim - 1
+    x = x_dev
+    for _ in range(W):
+        x = step(x, i)["sample"]
+        i -= 1
+    # ---- timed region 1: inputs resident in HBM -------------------------------------------------
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    vit_ops.PROFILE = []
+    k0 = _lib.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record()
+    for _ in range(K):
+        x = step(x, i)["sample"]
+        i -= 1
+    e1.record()
+    barrier()
+    wall1 = time.time()
+    ms = tmax(e0.elapsed_time(e1))
+    launches = _lib.kernel_launches - k0
+    prof, vit_ops.PROFILE = vit_ops.PROFILE, None
+    gemm_ms = sum(a.elapsed_time(b) for _, a, b in prof)
+    gemm_flops = sum(f for f, _, _ in prof)
+    clk = clocks.summary(wall0, wall1) if clocks else None
+    # ---- timed region 2: end to end through host buffers ------------------------------------------
+    barrier()
+    e0.record()
+    for _ in range(K):
+        xd = x_host.to(dev, non_blocking=True)
+        out = step(xd, i)
+        out_host[0].copy_(out["sample"][0], non_blocking=True)
+        out_host[1].copy_(out["pred_xstart"][0].float(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller consumes the step result (PNG every step, sample.py:290-295)
+        i -= 1
+        if i < 0:
+            i = ddim - 1
+    e1.record()
+    barrier()
+    ms_e2e = tmax(e0.elapsed_time(e1))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    tf_peak, hbm_peak, peak_src = measured_peaks()
+    value = K / (ms / 1e3)
+    e2e = K / (ms_e2e / 1e3)
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    line = {
+        "metric": "CLIP-guided DDIM steps/s @%dx%d" % (WORKLOADS[wl][0], WORKLOADS[wl][0]), "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": desc, "cutouts_per_step": cuts_per_step, "cutouts_per_rank": -(-cuts_per_step // world), "unet": "fp16 stock PyTorch, replicated",
+                   "clip": "bf16 operands / fp32 accumulate + fp32 residual stream, random init", "parallelism": "cutouts sharded x%d, 1 all-reduce/step" % world,
+                   "l2": "working set (1.1 GB UNet + ViT weights + activations) far exceeds the 126 MB L2; no flush"},
+        "cutouts_per_s": cuts_per_step * value,
+        "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM/TMA, all ViT GEMMs)", "achieved": achieved, "peak": tf_peak,
+                     "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None, "peak_source": peak_src, "launches": len(prof),
+                     "share_of_step": gemm_ms / ms if ms > 0 else None},
+    }
+    if world == 1 and not args.no_cpu_baseline and not clip_only:
+        torch.set_num_threads(os.cpu_count() or 1)
+        cstep, cx, cddim, _ = build_cpu_reference(args.workload)
+        t0 = time.time()
+        cstep(cx, cddim - 1)
+        dt = time.time() - t0
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "1 full guidance step of the same workload, fp32, no warm-up (%.1f s)" % dt}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -82,7 +82,10 @@ _SIGNATURES = {
 }
 
 _lib = None
-launch_count = 0  # kernels-launching C-ABI calls made through this module (bench.py reports it)
+launch_count = 0     # C-ABI calls made through this module
+kernel_launches = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
+# kernels launched per entry point (csrc/*.cu); 1 unless listed
+_KERNELS_PER_CALL = {"cg_cutouts_fwd": 4, "cg_cutouts_bwd": 4, "cg_attention_bwd": 3, "cg_grad_finalize": 2, "cg_any_nan": 2}
 
 
 class ClipGuideError(RuntimeError):
@@ -137,12 +140,13 @@ def stream_ptr():
 
 def call(name, *args):
     """Call an int-returning entry point on the current stream (appended as last argument)."""
-    global launch_count
+    global launch_count, kernel_launches
     lib = load()
     if name in lib._cg_missing:
         raise ClipGuideError("%s is not exported by %s: rebuild the library (stale build)" % (name, LIB_PATH))
     rc = getattr(lib, name)(*args, stream_ptr())
     launch_count += 1
+    kernel_launches += _KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
 
 
