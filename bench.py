@@ -286,7 +286,7 @@ def main():
     e2e = K / (ms_e2e / 1e3)
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     line = {
-        "metric": "CLIP-guided DDIM steps/s @%dx%d" % (WORKLOADS[wl][0], WORKLOADS[wl][0]), "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": "CLIP-guided DDIM steps/s @%dx%d" % (size, size), "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "cutouts_per_step": cuts_per_step, "cutouts_per_rank": -(-cuts_per_step // world), "unet": "fp16 stock PyTorch, replicated",
                    "clip": "bf16 operands / fp32 accumulate + fp32 residual stream, random init", "parallelism": "cutouts sharded x%d, 1 all-reduce/step" % world,

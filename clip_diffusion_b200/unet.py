@@ -144,7 +144,7 @@ class UNetModel(nn.Module):
         if use_fp16:
             for part in (self.input_blocks, self.middle_block, self.output_blocks):
                 for mod in part.modules():
-                    if isinstance(mod, (nn.Conv1d, nn.Conv2d, nn.Linear)):
+                    if isinstance(mod, (nn.Conv1d, nn.Conv2d)):  # as guided-diffusion: convs only, Linear stays fp32
                         mod.half()
 
     def forward(self, x, timesteps, y=None):
