@@ -247,6 +247,9 @@ def main():
     vit_ops.PROFILE = []
     k0 = _lib.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    use_range = os.environ.get("CG_BENCH_PROFILER_RANGE") == "1"  # ncu --profile-from-start off: profile the timed region only
+    if use_range:
+        torch.cuda.profiler.start()
     wall0 = time.time()
     e0.record()
     for _ in range(K):
@@ -254,6 +257,8 @@ def main():
         i -= 1
     e1.record()
     barrier()
+    if use_range:
+        torch.cuda.profiler.stop()
     wall1 = time.time()
     ms = tmax(e0.elapsed_time(e1))
     launches = _lib.kernel_launches - k0

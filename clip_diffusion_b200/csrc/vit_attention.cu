@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __nv_bfloat
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
+  if (qb * BR + warp * 16 >= T) return;  // this warp's 16 rows are all padding (no block-wide sync follows)
   uint32_t qa[4][4];
   load_a_frags(sQ, warp * 16, qa);
   float o[8][4];
@@ -114,10 +115,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __nv_bfloat
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      uint32_t b[4][2];
-      load_b_frags_nk(sK, kc + nt * 8, b);
+      if (kc + nt * 8 < T) {  // ragged tail: whole 8-key tiles beyond T are skipped (warp-uniform)
+        uint32_t b[4][2];
+        load_b_frags_nk(sK, kc + nt * 8, b);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) mma_bf16(s[nt], qa[kk], b[kk][0], b[kk][1]);
+        for (int kk = 0; kk < 4; ++kk) mma_bf16(s[nt], qa[kk], b[kk][0], b[kk][1]);
+      }
     }
     float mx0 = m0, mx1 = m1;
 #pragma unroll
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __nv_bfloat
     // O += P V : k = keys (4 steps of 16), n = d (8 groups of 8)
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
+      if (kc + kk * 16 >= T) continue;  // P is exactly 0 there
 #pragma unroll
       for (int cp = 0; cp < 4; ++cp) {
         uint32_t b00, b01, b10, b11;
@@ -214,6 +218,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const __nv_bfl
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
+  if (qb * BR + warp * 16 >= T) return;
   uint32_t qa[4][4], da[4][4];
   load_a_frags(sQ, warp * 16, qa);
   load_a_frags(sdO, warp * 16, da);
@@ -230,11 +235,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const __nv_bfl
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t bk[4][2], bv[4][2];
-      load_b_frags_nk(sK, kc + nt * 8, bk);
-      load_b_frags_nk(sV, kc + nt * 8, bv);
+      if (kc + nt * 8 < T) {
+        uint32_t bk[4][2], bv[4][2];
+        load_b_frags_nk(sK, kc + nt * 8, bk);
+        load_b_frags_nk(sV, kc + nt * 8, bv);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) { mma_bf16(s, qa[kk], bk[kk][0], bk[kk][1]); mma_bf16(dp, da[kk], bv[kk][0], bv[kk][1]); }
+        for (int kk = 0; kk < 4; ++kk) { mma_bf16(s, qa[kk], bk[kk][0], bk[kk][1]); mma_bf16(dp, da[kk], bv[kk][0], bv[kk][1]); }
+      }
       const int key = kc + nt * 8 + t4 * 2;
       const bool v0 = key < T, v1 = key + 1 < T;
       const float p0 = v0 ? __expf(s[0] * scale - lse0) : 0.f, p1 = v1 ? __expf(s[1] * scale - lse0) : 0.f;
@@ -244,6 +251,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const __nv_bfl
     }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
+      if (kc + kk * 16 >= T) continue;
 #pragma unroll
       for (int cp = 0; cp < 4; ++cp) {
         uint32_t b00, b01, b10, b11;
@@ -287,6 +295,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const __nv_bf
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
+  if (kb * BR + warp * 16 >= T) return;
   uint32_t ka[4][4], va[4][4];
   load_a_frags(sK, warp * 16, ka);
   load_a_frags(sV, warp * 16, va);
@@ -298,11 +307,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const __nv_bf
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t bq[4][2], bo[4][2];
-      load_b_frags_nk(sQ, qc + nt * 8, bq);
-      load_b_frags_nk(sdO, qc + nt * 8, bo);
+      if (qc + nt * 8 < T) {
+        uint32_t bq[4][2], bo[4][2];
+        load_b_frags_nk(sQ, qc + nt * 8, bq);
+        load_b_frags_nk(sdO, qc + nt * 8, bo);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) { mma_bf16(s, ka[kk], bq[kk][0], bq[kk][1]); mma_bf16(dp, va[kk], bo[kk][0], bo[kk][1]); }
+        for (int kk = 0; kk < 4; ++kk) { mma_bf16(s, ka[kk], bq[kk][0], bq[kk][1]); mma_bf16(dp, va[kk], bo[kk][0], bo[kk][1]); }
+      }
       const int q = qc + nt * 8 + t4 * 2;  // columns of the transposed tile are queries
       const bool v0 = q < T, v1 = q + 1 < T;
       const float ls0 = s_lse[q], ls1 = s_lse[q + 1], d0 = s_dl[q], d1 = s_dl[q + 1];
@@ -315,6 +326,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const __nv_bf
     }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
+      if (qc + kk * 16 >= T) continue;
 #pragma unroll
       for (int cp = 0; cp < 4; ++cp) {
         uint32_t b00, b01, b10, b11;

@@ -7,8 +7,10 @@
 //     overlaps the main loop of tile i+1;
 //   * persistent: one CTA per SM walks the tile list (tile = blockIdx.x + i*gridDim.x), consecutive
 //     tiles share the A row-block so it is reused out of L2;
-//   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (tcgen05.ld ->
-//     registers -> bias / QuickGELU / residual -> global).
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue (tcgen05.ld ->
+//     registers -> bias / QuickGELU / residual -> global).  Eight epilogue warps = two per scheduler and per
+//     TMEM lane quarter (each takes half of the tile's columns): one warp per scheduler cannot hide its own ALU
+//     latency and made the QuickGELU epilogues 2-3x slower than the main loop (profiles/r01_*).
 //
 // Weights are frozen (models.py:71), so every GEMM of the backward pass is a dgrad with a pre-transposed
 // weight copy: all calls have both operands K-major and share this one kernel.
@@ -22,7 +24,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int STAGES = 4;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
 
 struct GemmArgs {
   int M, N, K;
@@ -110,10 +113,16 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-__device__ __forceinline__ float qgelu(float u) { return u / (1.f + __expf(-1.702f * u)); }
+// sigmoid(1.702 u) = 0.5 * tanh(0.851 u) + 0.5 : one MUFU op instead of ex2 + a full-precision division
+__device__ __forceinline__ float sigmoid_1702(float u) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * u));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float qgelu(float u) { return u * sigmoid_1702(u); }
 __device__ __forceinline__ float qgelu_grad(float u) {
-  const float s = 1.f / (1.f + __expf(-1.702f * u));
-  return s * (1.f + 1.702f * u * (1.f - s));
+  const float s = sigmoid_1702(u);
+  return s * fmaf(1.702f * u, 1.f - s, 1.f);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tn_kernel(const __gr
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -279,7 +288,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tn_kernel(const __gr
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int q = warp & 3;             // TMEM lane quarter this warp may touch (warp id % 4)
+    const int chalf = (warp - 4) >> 2;  // which half of the tile's columns this warp drains
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tn_kernel(const __gr
       if (EPI == CG_EPI_PATCH_POS_F32) orow = (row / g.g2) * (g.g2 + 1) + 1 + row % g.g2;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         uint32_t acc[32];
         tmem_ld32(t_row + (uint32_t)c, acc);
         tmem_ld_wait();
