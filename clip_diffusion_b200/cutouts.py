@@ -136,6 +136,7 @@ class Cutouts(nn.Module):
         self.last_record = None  # the RNG record of the most recent call (crop sizes / offsets / flags)
 
     def forward(self, input, _input01=True):
+        _lib.require_cuda(input)
         rec = _draw(input, self.cut_size, self.num_overview_cuts, self.num_inner_cuts, self.inner_cut_size_power, self.cut_gray_portion)
         self.last_record = rec
         return _CutoutsFn.apply(input, rec, _input01)
