@@ -9,6 +9,8 @@
 //
 // All the randomness arrives as plain numbers (cg_cut_t / cg_aug_t) drawn on the host in the reference's
 // order (clip_diffusion_b200/rng_record.py), which is what makes crop sizes/offsets bit-exact.
+#include <string.h>
+#include <vector>
 #include "common.cuh"
 
 namespace {
@@ -20,7 +22,9 @@ constexpr int MAX_SIZE = 1024;
 constexpr float GW0 = 0.2989f, GW1 = 0.587f, GW2 = 0.114f;  // torchvision rgb_to_grayscale
 
 struct WsLayout {
-  size_t cuts, aug, taps, left, wfw, tstart, wtr, base, z, scratch, partial, spartial, total;
+  // metadata block (filled by ONE host-to-device copy): header | cuts[N] | aug | uidx[N] | ucuts[N] | dupoff[N+1] | duplist[N]
+  size_t cuts, aug, uidx, ucuts, dupoff, duplist, meta_end;
+  size_t taps, left, wfw, tstart, wtr, base, z, scratch, partial, spartial, total;
   int nblk;
 };
 
@@ -31,6 +35,12 @@ WsLayout ws_layout(int N, int cs, int max_size) {
   size_t o = 256;  // header
   L.cuts = o; o = align_up(o + sizeof(cg_cut_t) * N, 256);
   L.aug = o; o = align_up(o + sizeof(cg_aug_t), 256);
+  L.uidx = o; o = align_up(o + sizeof(int) * N, 256);
+  L.ucuts = o; o = align_up(o + sizeof(cg_cut_t) * N, 256);
+  L.dupoff = o; o = align_up(o + sizeof(int) * (N + 1), 256);
+  L.duplist = o; o = align_up(o + sizeof(int) * N, 256);
+  L.meta_end = o;
+  // per UNIQUE crop geometry (<= N): resize tables and the base (resampled) cutout
   L.taps = o; o = align_up(o + sizeof(int) * N, 256);
   L.left = o; o = align_up(o + sizeof(int) * (size_t)N * cs, 256);
   L.wfw = o; o = align_up(o + sizeof(float) * (size_t)N * cs * TAPS_MAX, 256);
@@ -48,7 +58,7 @@ WsLayout ws_layout(int N, int cs, int max_size) {
 }
 
 struct WsHeader {
-  int magic, N, cs, max_size, H, W, fwd_done, pad;
+  int magic, N, cs, max_size, H, W, U, input01;  // U = number of unique crop geometries
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -70,6 +80,7 @@ __global__ void __launch_bounds__(256) tables_kernel(const cg_cut_t* __restrict_
                                                      int* __restrict__ tstart, float* __restrict__ wtr) {
   extern __shared__ int s_left[];  // cs ints
   const int n = blockIdx.x;
+  if (n >= N) return;
   const int size = cuts[n].size;
   const double scale_d = (double)cs / (double)size;
   const float scale = (float)scale_d;
@@ -143,12 +154,15 @@ __global__ void __launch_bounds__(256) tables_kernel(const cg_cut_t* __restrict_
 // (smem -> base).  x_in is tiny (3 MB at 512^2) and stays L2 resident; reads are coalesced along x.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) resample_fwd_kernel(const float* __restrict__ x_in, int H, int W,
-                                                           const cg_cut_t* __restrict__ cuts, const int* __restrict__ tapsN,
+                                                           const cg_cut_t* __restrict__ cuts, int U, const int* __restrict__ tapsN,
                                                            const int* __restrict__ left, const float* __restrict__ wfw, int cs,
                                                            int input01, float* __restrict__ base) {
   __shared__ float tmp[RT][MAX_SIZE];
+  __shared__ float s_w[RT][TAPS_MAX];
+  __shared__ int s_l[RT];
   const float ka = input01 ? 0.f : 1.f, km = input01 ? 1.f : 0.5f;  // (x + ka) * km
-  const int n = blockIdx.y;
+  const int n = blockIdx.y;  // unique crop index
+  if (n >= U) return;
   const int r0 = blockIdx.x * RT;
   const cg_cut_t cut = cuts[n];
   const int size = cut.size, taps = tapsN[n];
@@ -159,35 +173,49 @@ __global__ void __launch_bounds__(256) resample_fwd_kernel(const float* __restri
   const bool hflip = cut.flags & CG_CUT_HFLIP;
   const size_t plane = (size_t)H * W;
   float* bn = base + (size_t)n * 3 * cs * cs;
+  // weights / first tap of this CTA's RT output rows
+  for (int i = threadIdx.x; i < RT * TAPS_MAX; i += blockDim.x) {
+    const int r = i / TAPS_MAX, t = i - r * TAPS_MAX;
+    const int oy = r0 + r;
+    s_w[r][t] = (oy < cs && t < taps) ? wf[(size_t)oy * TAPS_MAX + t] : 0.f;
+    if (t == 0) s_l[r] = oy < cs ? lf[oy] : 0;
+  }
+  __syncthreads();
+  const int row_lo = s_l[0];
+  const int last_r = min(RT, cs - r0) - 1;
+  const int row_hi = s_l[last_r] + taps;  // exclusive, crop coordinates
   const int nch = gray_pre ? 1 : 3;
   for (int ch = 0; ch < nch; ++ch) {
-    for (int idx = threadIdx.x; idx < RT * size; idx += blockDim.x) {
-      const int r = idx / size, lx = idx - r * size;
-      const int oy = r0 + r;
-      float acc = 0.f;
+    // vertical pass: one thread owns a crop column, walks the source rows ONCE (coalesced across the warp) and
+    // feeds the <= RT output-row accumulators that tap each row
+    for (int lx = threadIdx.x; lx < size; lx += blockDim.x) {
+      float acc[RT];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) acc[r] = 0.f;
       const int sx = cut.x0 + lx;
-      if (oy < cs && sx >= 0 && sx < W) {
-        const int ly0 = lf[oy];
-        const float* w = wf + (size_t)oy * TAPS_MAX;
-        for (int t = 0; t < taps; ++t) {
-          const int ly = ly0 + t;
+      if (sx >= 0 && sx < W) {
+        for (int ly = max(row_lo, 0); ly < min(row_hi, size); ++ly) {
           const int sy = cut.y0 + ly;
-          if (ly >= 0 && ly < size && sy >= 0 && sy < H) {
-            float v;
-            const size_t off = (size_t)sy * W + sx;
-            if (gray_pre) {
-              const float rr = (__ldg(x_in + off) + ka) * km;
-              const float gg = (__ldg(x_in + plane + off) + ka) * km;
-              const float bb = (__ldg(x_in + 2 * plane + off) + ka) * km;
-              v = __fadd_rn(__fadd_rn(__fmul_rn(GW0, rr), __fmul_rn(GW1, gg)), __fmul_rn(GW2, bb));
-            } else {
-              v = (__ldg(x_in + ch * plane + off) + ka) * km;
-            }
-            acc = fmaf(w[t], v, acc);
+          if (sy < 0 || sy >= H) continue;
+          const size_t off = (size_t)sy * W + sx;
+          float v;
+          if (gray_pre) {
+            const float rr = (__ldg(x_in + off) + ka) * km;
+            const float gg = (__ldg(x_in + plane + off) + ka) * km;
+            const float bb = (__ldg(x_in + 2 * plane + off) + ka) * km;
+            v = __fadd_rn(__fadd_rn(__fmul_rn(GW0, rr), __fmul_rn(GW1, gg)), __fmul_rn(GW2, bb));
+          } else {
+            v = (__ldg(x_in + ch * plane + off) + ka) * km;
+          }
+#pragma unroll
+          for (int r = 0; r < RT; ++r) {
+            const int t = ly - s_l[r];
+            if (t >= 0 && t < taps) acc[r] = fmaf(s_w[r][t], v, acc[r]);
           }
         }
       }
-      tmp[r][lx] = acc;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) tmp[r][lx] = acc[r];
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < RT * cs; idx += blockDim.x) {
@@ -455,8 +483,9 @@ __device__ __forceinline__ void affine_src(const AffineCoef& a, int cs, int ox, 
 
 // F2: augment up to the pre-jitter image z, plus the partial sums of the contrast mean.
 // grid (nblk, N), 256 threads, one output pixel (3 channels) per thread.
-__global__ void __launch_bounds__(256) augment_fwd_kernel(const float* __restrict__ base, const cg_aug_t* __restrict__ augp, NoiseSrc ns,
-                                                          int cs, float* __restrict__ z, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) augment_fwd_kernel(const float* __restrict__ base, const int* __restrict__ uidx,
+                                                          const cg_aug_t* __restrict__ augp, NoiseSrc ns, int cs, float* __restrict__ z,
+                                                          float* __restrict__ partial) {
   __shared__ float red[32];
   __shared__ cg_aug_t aug;
   if (threadIdx.x < sizeof(cg_aug_t) / 4) reinterpret_cast<int*>(&aug)[threadIdx.x] = reinterpret_cast<const int*>(augp)[threadIdx.x];
@@ -464,7 +493,7 @@ __global__ void __launch_bounds__(256) augment_fwd_kernel(const float* __restric
   const int n = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t pp = (size_t)cs * cs;
-  const float* bn = base + (size_t)n * 3 * pp;
+  const float* bn = base + (size_t)uidx[n] * 3 * pp;  // identical crops (e.g. > 4 overview cuts) share one base
   float v[3] = {0.f, 0.f, 0.f};
   float gsum = 0.f;
   if (pix < cs * cs) {
@@ -522,9 +551,9 @@ __device__ __forceinline__ size_t patch_offset(int n, int oy, int ox, int c, int
 }
 
 // F3: jitter + normalise + layout.  src = z (augment on) or base (augment off).
-__global__ void __launch_bounds__(256) jitter_fwd_kernel(const float* __restrict__ src, const cg_aug_t* __restrict__ augp,
-                                                         const float* __restrict__ partial, int nblk, int cs, void* __restrict__ out,
-                                                         int fmt, int patch, int kpad) {
+__global__ void __launch_bounds__(256) jitter_fwd_kernel(const float* __restrict__ src, const int* __restrict__ uidx,
+                                                         const cg_aug_t* __restrict__ augp, const float* __restrict__ partial, int nblk,
+                                                         int cs, void* __restrict__ out, int fmt, int patch, int kpad) {
   __shared__ float red[32];
   __shared__ cg_aug_t aug;
   if (threadIdx.x < sizeof(cg_aug_t) / 4) reinterpret_cast<int*>(&aug)[threadIdx.x] = reinterpret_cast<const int*>(augp)[threadIdx.x];
@@ -535,7 +564,7 @@ __global__ void __launch_bounds__(256) jitter_fwd_kernel(const float* __restrict
   if (aug.augment) mean = cut_mean(partial, n, nblk, cs, red);
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= cs * cs) return;
-  const float* sn = src + (size_t)n * 3 * pp + pix;
+  const float* sn = src + (size_t)(aug.augment ? n : uidx[n]) * 3 * pp + pix;
   float v[3] = {sn[0], sn[pp], sn[2 * pp]};
   if (aug.augment) {
     JitterParams jp = {{aug.perm[0], aug.perm[1], aug.perm[2], aug.perm[3]}, aug.brightness, aug.contrast, aug.saturation, aug.hue};
@@ -633,14 +662,64 @@ __global__ void __launch_bounds__(256) jitter_bwd_kernel(const void* __restrict_
   }
 }
 
-// B2: affine backward as a gather: base pixel (y, xb) collects from the <= 3x3 output pixels whose bilinear
-// footprint contains it.  Writes d(base) (flip undone).
-__global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict__ da, const cg_aug_t* __restrict__ augp, int cs,
-                                                         float* __restrict__ dbase) {
+// B1 (pass 1, de-duplicated): grid (nblk, U).  The affine map and the resampling are linear and identical for cutouts
+// that share a crop geometry (the "> 4 overview cuts" case: N identical crops, cutouts.py:77-79), so their gradients
+// are summed HERE, right after the non-linear jitter backward, and everything downstream runs once per unique crop.
+__global__ void __launch_bounds__(256) jitter_bwd_sum_kernel(const void* __restrict__ dout, const float* __restrict__ z,
+                                                             const cg_aug_t* __restrict__ augp, const float* __restrict__ partial,
+                                                             const float* __restrict__ spartial, const int* __restrict__ hdr,
+                                                             const int* __restrict__ dupoff, const int* __restrict__ duplist, int nblk, int cs,
+                                                             int fmt, int patch, int kpad, float* __restrict__ da) {
+  __shared__ float red[32];
   __shared__ cg_aug_t aug;
   if (threadIdx.x < sizeof(cg_aug_t) / 4) reinterpret_cast<int*>(&aug)[threadIdx.x] = reinterpret_cast<const int*>(augp)[threadIdx.x];
   __syncthreads();
-  const int n = blockIdx.y;
+  const int u = blockIdx.y;
+  if (u >= hdr[6]) return;  // WsHeader.U
+  const size_t pp = (size_t)cs * cs;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = pix < cs * cs;
+  JitterParams jp = {{aug.perm[0], aug.perm[1], aug.perm[2], aug.perm[3]}, aug.brightness, aug.contrast, aug.saturation, aug.hue};
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int k = dupoff[u]; k < dupoff[u + 1]; ++k) {
+    const int n = duplist[k];
+    float d[3] = {0.f, 0.f, 0.f};
+    if (active) {
+      load_dout(dout, fmt, n, pix, cs, patch, kpad, d);
+      if (aug.normalize) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d[c] = d[c] / aug.stdv[c];
+      }
+    }
+    if (aug.augment) {
+      const float mean = cut_mean(partial, n, nblk, cs, red);
+      float a = 0.f;
+      for (int i = threadIdx.x; i < nblk; i += blockDim.x) a += spartial[(size_t)n * nblk + i];
+      const float S_over_n = block_sum(a, red) / (float)(cs * cs);
+      if (active) {
+        const float* zn = z + (size_t)n * 3 * pp + pix;
+        const float zin[3] = {zn[0], zn[pp], zn[2 * pp]};
+        jitter_bwd_range(jp, 0, 4, mean, zin, d, true, S_over_n);
+        if (aug.gray) { const float g = d[0] + d[1] + d[2]; d[0] = GW0 * g; d[1] = GW1 * g; d[2] = GW2 * g; }
+      }
+    }
+    acc[0] += d[0]; acc[1] += d[1]; acc[2] += d[2];
+  }
+  if (active) {
+    float* o = da + (size_t)u * 3 * pp + pix;
+    o[0] = acc[0]; o[pp] = acc[1]; o[2 * pp] = acc[2];
+  }
+}
+
+// B2: affine backward as a gather: base pixel (y, xb) collects from the <= 3x3 output pixels whose bilinear
+// footprint contains it.  Writes d(base) (flip undone).
+__global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict__ da, const cg_aug_t* __restrict__ augp,
+                                                         const int* __restrict__ hdr, int cs, float* __restrict__ dbase) {
+  __shared__ cg_aug_t aug;
+  if (threadIdx.x < sizeof(cg_aug_t) / 4) reinterpret_cast<int*>(&aug)[threadIdx.x] = reinterpret_cast<const int*>(augp)[threadIdx.x];
+  __syncthreads();
+  const int n = blockIdx.y;  // unique crop index
+  if (n >= hdr[6]) return;
   const size_t pp = (size_t)cs * cs;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= cs * cs) return;
@@ -687,7 +766,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict
 
 // B3: transposed resample, gather over SOURCE pixels.  grid (ceil(W/32), ceil(H/8)), block (32, 8).
 // Every thread owns one pixel of d(x_in) (3 channels) and loops over the cutouts covering it.
-__global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restrict__ dbase, const cg_cut_t* __restrict__ cuts, int N,
+__global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restrict__ dbase, const cg_cut_t* __restrict__ cuts, const int* __restrict__ hdr,
                                                            const int* __restrict__ tstart, const float* __restrict__ wtr, int cs,
                                                            int max_size, int H, int W, float coef, int accumulate,
                                                            float* __restrict__ dx_in) {
@@ -695,6 +774,7 @@ __global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restri
   const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 8;
   const size_t pp = (size_t)cs * cs;
   float acc[3] = {0.f, 0.f, 0.f};
+  const int N = hdr[6];  // unique crops only: duplicates were summed in jitter_bwd_sum_kernel
   for (int n = 0; n < N; ++n) {
     const cg_cut_t cut = cuts[n];
     // tile-uniform rejection
@@ -765,11 +845,37 @@ extern "C" int cg_cutouts_fwd(const float* x_in, int H, int W, const cg_cut_t* c
   const WsLayout L = ws_layout(N, cs, max_size);
   char* ws = reinterpret_cast<char*>(workspace);
   cudaStream_t s = cg_stream(stream);
-  WsHeader hdr = {0x43475753, N, cs, max_size, H, W, 1, aug_h->input01};
-  CG_CUDA(cudaMemcpyAsync(ws, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, s));
-  CG_CUDA(cudaMemcpyAsync(ws + L.cuts, cuts_h, sizeof(cg_cut_t) * N, cudaMemcpyHostToDevice, s));
-  CG_CUDA(cudaMemcpyAsync(ws + L.aug, aug_h, sizeof(cg_aug_t), cudaMemcpyHostToDevice, s));
-  const cg_cut_t* cuts = reinterpret_cast<const cg_cut_t*>(ws + L.cuts);
+  // ---- metadata block, built on the host and shipped with ONE copy: header, cuts, aug, unique-crop tables
+  std::vector<char> meta(L.meta_end, 0);
+  cg_cut_t* ucuts_h = reinterpret_cast<cg_cut_t*>(meta.data() + L.ucuts);
+  int* uidx_h = reinterpret_cast<int*>(meta.data() + L.uidx);
+  int* dupoff_h = reinterpret_cast<int*>(meta.data() + L.dupoff);
+  int* duplist_h = reinterpret_cast<int*>(meta.data() + L.duplist);
+  int U = 0;
+  for (int i = 0; i < N; ++i) {
+    int u = 0;
+    for (; u < U; ++u)
+      if (ucuts_h[u].y0 == cuts_h[i].y0 && ucuts_h[u].x0 == cuts_h[i].x0 && ucuts_h[u].size == cuts_h[i].size &&
+          ((ucuts_h[u].flags ^ cuts_h[i].flags) & (CG_CUT_GRAY_PRE | CG_CUT_GRAY_POST | CG_CUT_HFLIP)) == 0)
+        break;
+    if (u == U) ucuts_h[U++] = cuts_h[i];
+    uidx_h[i] = u;
+  }
+  {  // CSR of the duplicates of every unique crop
+    std::vector<int> cnt(U + 1, 0);
+    for (int i = 0; i < N; ++i) cnt[uidx_h[i] + 1]++;
+    for (int u = 0; u < U; ++u) cnt[u + 1] += cnt[u];
+    for (int u = 0; u <= U; ++u) dupoff_h[u] = cnt[u];
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+    for (int i = 0; i < N; ++i) duplist_h[fill[uidx_h[i]]++] = i;
+  }
+  WsHeader hdr = {0x43475753, N, cs, max_size, H, W, U, aug_h->input01};
+  memcpy(meta.data(), &hdr, sizeof(hdr));
+  memcpy(meta.data() + L.cuts, cuts_h, sizeof(cg_cut_t) * N);
+  memcpy(meta.data() + L.aug, aug_h, sizeof(cg_aug_t));
+  CG_CUDA(cudaMemcpyAsync(ws, meta.data(), L.meta_end, cudaMemcpyHostToDevice, s));  // pageable source: staged before returning
+  const cg_cut_t* ucuts = reinterpret_cast<const cg_cut_t*>(ws + L.ucuts);
+  const int* uidx = reinterpret_cast<const int*>(ws + L.uidx);
   const cg_aug_t* aug = reinterpret_cast<const cg_aug_t*>(ws + L.aug);
   int* taps = reinterpret_cast<int*>(ws + L.taps);
   int* left = reinterpret_cast<int*>(ws + L.left);
@@ -780,17 +886,17 @@ extern "C" int cg_cutouts_fwd(const float* x_in, int H, int W, const cg_cut_t* c
   float* z = reinterpret_cast<float*>(ws + L.z);
   float* partial = reinterpret_cast<float*>(ws + L.partial);
 
-  tables_kernel<<<N, 256, sizeof(int) * cs, s>>>(cuts, N, cs, max_size, taps, left, wfw, tstart, wtr);
+  tables_kernel<<<U, 256, sizeof(int) * cs, s>>>(ucuts, U, cs, max_size, taps, left, wfw, tstart, wtr);
   CG_LAUNCH_CHECK();
-  resample_fwd_kernel<<<dim3((cs + RT - 1) / RT, N), 256, 0, s>>>(x_in, H, W, cuts, taps, left, wfw, cs, aug_h->input01, base);
+  resample_fwd_kernel<<<dim3((cs + RT - 1) / RT, U), 256, 0, s>>>(x_in, H, W, ucuts, U, taps, left, wfw, cs, aug_h->input01, base);
   CG_LAUNCH_CHECK();
   dim3 grid(L.nblk, N);
   if (aug_h->augment) {
     NoiseSrc ns = {noise, aug_h->noise_seed, aug_h->cut_index0, N, cs, aug_h->noise_std};
-    augment_fwd_kernel<<<grid, 256, 0, s>>>(base, aug, ns, cs, z, partial);
+    augment_fwd_kernel<<<grid, 256, 0, s>>>(base, uidx, aug, ns, cs, z, partial);
     CG_LAUNCH_CHECK();
   }
-  jitter_fwd_kernel<<<grid, 256, 0, s>>>(aug_h->augment ? z : base, aug, partial, L.nblk, cs, out, fmt, patch, kpad);
+  jitter_fwd_kernel<<<grid, 256, 0, s>>>(aug_h->augment ? z : base, uidx, aug, partial, L.nblk, cs, out, fmt, patch, kpad);
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -804,7 +910,10 @@ extern "C" int cg_cutouts_bwd(const void* dout, int H, int W, int N, int cs, int
   const WsLayout L = ws_layout(N, cs, max_size);
   char* ws = reinterpret_cast<char*>(workspace);
   cudaStream_t s = cg_stream(stream);
-  const cg_cut_t* cuts = reinterpret_cast<const cg_cut_t*>(ws + L.cuts);
+  const cg_cut_t* ucuts = reinterpret_cast<const cg_cut_t*>(ws + L.ucuts);
+  const int* hdr = reinterpret_cast<const int*>(ws);
+  const int* dupoff = reinterpret_cast<const int*>(ws + L.dupoff);
+  const int* duplist = reinterpret_cast<const int*>(ws + L.duplist);
   const cg_aug_t* aug = reinterpret_cast<const cg_aug_t*>(ws + L.aug);
   int* tstart = reinterpret_cast<int*>(ws + L.tstart);
   float* wtr = reinterpret_cast<float*>(ws + L.wtr);
@@ -813,14 +922,16 @@ extern "C" int cg_cutouts_bwd(const void* dout, int H, int W, int N, int cs, int
   float* scratch = reinterpret_cast<float*>(ws + L.scratch);
   float* partial = reinterpret_cast<float*>(ws + L.partial);
   float* spartial = reinterpret_cast<float*>(ws + L.spartial);
+  // The number of unique crops U lives in the device-side header (this call does not see the host structs): the
+  // per-unique kernels are launched over N slots and slots >= U exit immediately.
   dim3 grid(L.nblk, N);
   jitter_bwd_kernel<0><<<grid, 256, 0, s>>>(dout, z, aug, partial, spartial, L.nblk, cs, fmt, patch, kpad, scratch);
   CG_LAUNCH_CHECK();
-  jitter_bwd_kernel<1><<<grid, 256, 0, s>>>(dout, z, aug, partial, spartial, L.nblk, cs, fmt, patch, kpad, scratch);
+  jitter_bwd_sum_kernel<<<grid, 256, 0, s>>>(dout, z, aug, partial, spartial, hdr, dupoff, duplist, L.nblk, cs, fmt, patch, kpad, scratch);
   CG_LAUNCH_CHECK();
-  affine_bwd_kernel<<<grid, 256, 0, s>>>(scratch, aug, cs, base);
+  affine_bwd_kernel<<<grid, 256, 0, s>>>(scratch, aug, hdr, cs, base);
   CG_LAUNCH_CHECK();
-  resample_bwd_kernel<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, s>>>(base, cuts, N, tstart, wtr, cs, max_size, H, W,
+  resample_bwd_kernel<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, s>>>(base, ucuts, hdr, tstart, wtr, cs, max_size, H, W,
                                                                               input01 ? coef : 0.5f * coef, accumulate, dx_in);
   CG_LAUNCH_CHECK();
   return 0;
