@@ -2,9 +2,11 @@
 // (cutout, head) problems), forward and dgrad.  Scores never touch HBM.
 //
 // Layout: packed qkv [Nimg*T, 3*D] bf16 (q | k | v; head h = columns h*64..h*64+63 of each third).
-// One CTA = 64 query (or key) rows of one (image, head); the whole K/V (or Q/dO) of that head sits in shared
-// memory (<= 640 x 64 bf16 each, XOR-swizzled 16-byte chunks so ldmatrix is conflict free); each of the 4 warps
-// owns 16 rows and keeps its accumulators in registers (mma.sync m16n8k16 bf16, fp32 accumulate).
+// One CTA = one (image, head): the whole K/V (forward, dQ) or Q/dO (dK/dV) of that head is loaded into shared
+// memory ONCE (<= 640 x 64 bf16 each, XOR-swizzled 16-byte chunks so ldmatrix is conflict free); its W warps walk
+// the 16-row tiles of the other operand (tile = warp, warp+W, ...; W chosen per T so that ceil(T/16) tiles fill
+// the warps with < 8% idle slots), staging each tile through a private 2 KB buffer and keeping the accumulators in
+// registers (mma.sync m16n8k16 bf16, fp32 accumulate).  Ragged tails are skipped at 8-key granularity.
 // These are ~5% of the tower's FLOPs; the dense GEMMs run on tcgen05 (vit_gemm.cu).
 //
 // backward = delta kernel (rowsum dO*O) + dQ kernel (per query block) + dK/dV kernel (per key block): P is
@@ -14,8 +16,7 @@
 namespace {
 
 constexpr int HD = 64;       // head dim
-constexpr int BR = 64;       // rows per CTA (4 warps x 16)
-constexpr int ATT_THREADS = 128;
+constexpr int MAX_WARPS = 8;
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,7 +49,19 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // Load `rows` rows (row r = global row row0 + r, valid if < T) x 64 columns starting at `src` (row stride ld) into a
 // swizzled smem tile.  All threads participate.
 __device__ __forceinline__ void load_tile(uint32_t dst, const __nv_bfloat16* src, long long ld, int row0, int rows, int T) {
-  for (int i = threadIdx.x; i < rows * 8; i += ATT_THREADS) {
+  for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    const bool ok = row0 + r < T;
+    cp_async16(dst + swz(r, c), src + (long long)(ok ? row0 + r : 0) * ld + c * 8, ok);
+  }
+}
+
+// One warp stages a 16-row tile (rows row0..row0+15 of src, zero beyond T) into its private buffer and waits for it.
+__device__ __forceinline__ void warp_stage_tile16(uint32_t dst, const __nv_bfloat16* src, long long ld, int row0, int T) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();  // every lane is done reading the previous tile
+#pragma unroll
+  for (int i = lane; i < 128; i += 32) {
     const int r = i >> 3, c = i & 7;
     const bool ok = row0 + r < T;
     cp_async16(dst + swz(r, c), src + (long long)(ok ? row0 + r : 0) * ld + c * 8, ok);
@@ -85,26 +98,27 @@ __device__ __forceinline__ void load_b_frags_kn(uint32_t tile, int k0, int cpair
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, float scale_log2,
-                                                               __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
+__global__ void __launch_bounds__(MAX_WARPS * 32) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, float scale_log2,
+                                                                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Tp = (T + 63) & ~63;
   const int D = heads * HD;
   const long long ld = 3LL * D;
-  const int qb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const uint32_t sQ = smem_addr(smem), sK = sQ + BR * 128, sV = sK + Tp * 128;
+  const int h = blockIdx.x, n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const uint32_t sK = smem_addr(smem), sV = sK + Tp * 128, sQ = sV + Tp * 128 + warp * 2048;
   const __nv_bfloat16* base = qkv + (long long)n * T * ld + h * HD;
-  load_tile(sQ, base, ld, qb * BR, BR, T);
   load_tile(sK, base + D, ld, 0, Tp, T);
   load_tile(sV, base + 2 * D, ld, 0, Tp, T);
   cp_async_wait_all();
   __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  if (qb * BR + warp * 16 >= T) return;  // this warp's 16 rows are all padding (no block-wide sync follows)
+  for (int r0 = warp * 16; r0 < T; r0 += nwarps * 16) {
+  warp_stage_tile16(sQ, base, ld, r0, T);
+  cp_async_wait_all();
+  __syncwarp();
   uint32_t qa[4][4];
-  load_a_frags(sQ, warp * 16, qa);
+  load_a_frags(sQ, 0, qa);
   float o[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
@@ -162,7 +176,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __nv_bfloat
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const int q0 = qb * BR + warp * 16 + g, q1 = q0 + 8;
+  const int q0 = r0 + g, q1 = q0 + 8;
   const float i0 = 1.f / l0, i1 = 1.f / l1;
   __nv_bfloat16* cb = ctx + (long long)n * T * D + h * HD;
 #pragma unroll
@@ -177,6 +191,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __nv_bfloat
     if (q0 < T) lb[q0] = m0 * scale_log2 / LOG2E + logf(l0);
     if (q1 < T) lb[q1] = m1 * scale_log2 / LOG2E + logf(l1);
   }
+  }  // tile loop
 }
 
 // ---------------------------------------------------------------------------------------------- backward
@@ -200,31 +215,34 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 }
 
 // dQ: CTA = 64 queries; K, V whole in smem.  dS = P*(dP - delta)*scale;  dQ = dS K.
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx,
-                                                                  const float* __restrict__ lse, const float* __restrict__ delta, int T, int heads,
-                                                                  float scale, __nv_bfloat16* __restrict__ dqkv) {
+__global__ void __launch_bounds__(MAX_WARPS * 32) attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx,
+                                                                    const float* __restrict__ lse, const float* __restrict__ delta, int T, int heads,
+                                                                    float scale, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Tp = (T + 63) & ~63;
   const int D = heads * HD;
   const long long ld = 3LL * D;
-  const int qb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const uint32_t sQ = smem_addr(smem), sdO = sQ + BR * 128, sK = sdO + BR * 128, sV = sK + Tp * 128;
+  const int h = blockIdx.x, n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const uint32_t sK = smem_addr(smem), sV = sK + Tp * 128, sQ = sV + Tp * 128 + warp * 4096, sdO = sQ + 2048;
   const __nv_bfloat16* base = qkv + (long long)n * T * ld + h * HD;
-  load_tile(sQ, base, ld, qb * BR, BR, T);
-  load_tile(sdO, dctx + (long long)n * T * D + h * HD, D, qb * BR, BR, T);
+  const __nv_bfloat16* dbase = dctx + (long long)n * T * D + h * HD;
   load_tile(sK, base + D, ld, 0, Tp, T);
   load_tile(sV, base + 2 * D, ld, 0, Tp, T);
   cp_async_wait_all();
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  if (qb * BR + warp * 16 >= T) return;
-  uint32_t qa[4][4], da[4][4];
-  load_a_frags(sQ, warp * 16, qa);
-  load_a_frags(sdO, warp * 16, da);
-  const int q0 = qb * BR + warp * 16 + g, q1 = q0 + 8;
   const float* lb = lse + ((long long)n * heads + h) * T;
   const float* db = delta + ((long long)n * heads + h) * T;
+  for (int r0 = warp * 16; r0 < T; r0 += nwarps * 16) {
+  warp_stage_tile16(sQ, base, ld, r0, T);
+  warp_stage_tile16(sdO, dbase, D, r0, T);
+  cp_async_wait_all();
+  __syncwarp();
+  uint32_t qa[4][4], da[4][4];
+  load_a_frags(sQ, 0, qa);
+  load_a_frags(sdO, 0, da);
+  const int q0 = r0 + g, q1 = q0 + 8;
   const float lse0 = q0 < T ? lb[q0] : 0.f, lse1 = q1 < T ? lb[q1] : 0.f;
   const float dl0 = q0 < T ? db[q0] : 0.f, dl1 = q1 < T ? db[q1] : 0.f;
   float dq[8][4];
@@ -268,37 +286,41 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const __nv_bfl
     if (q0 < T) *reinterpret_cast<uint32_t*>(ob + (long long)q0 * ld + d) = pack2(dq[nt][0], dq[nt][1]);
     if (q1 < T) *reinterpret_cast<uint32_t*>(ob + (long long)q1 * ld + d) = pack2(dq[nt][2], dq[nt][3]);
   }
+  }  // tile loop
 }
 
 // dK, dV: CTA = 64 keys; Q, dO whole in smem (+ lse, delta).  Works on the transposed problem:
 // S^T = K Q^T, P^T = exp(S^T*scale - lse[q]);  dV = P^T dO;  dP^T = V dO^T;  dS^T = P^T*(dP^T - delta[q])*scale;  dK = dS^T Q.
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx,
-                                                                   const float* __restrict__ lse, const float* __restrict__ delta, int T, int heads,
-                                                                   float scale, __nv_bfloat16* __restrict__ dqkv) {
+__global__ void __launch_bounds__(MAX_WARPS * 32) attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx,
+                                                                     const float* __restrict__ lse, const float* __restrict__ delta, int T, int heads,
+                                                                     float scale, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Tp = (T + 63) & ~63;
   const int D = heads * HD;
   const long long ld = 3LL * D;
-  const int kb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const uint32_t sK = smem_addr(smem), sV = sK + BR * 128, sQ = sV + BR * 128, sdO = sQ + Tp * 128;
-  float* s_lse = reinterpret_cast<float*>(smem + (size_t)(2 * BR + 2 * Tp) * 128);
+  const int h = blockIdx.x, n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const uint32_t sQ = smem_addr(smem), sdO = sQ + Tp * 128;
+  float* s_lse = reinterpret_cast<float*>(smem + (size_t)(2 * Tp) * 128);
   float* s_dl = s_lse + Tp;
+  const uint32_t sK = sdO + Tp * 128 + 2 * Tp * 4 + warp * 4096, sV = sK + 2048;
   const __nv_bfloat16* base = qkv + (long long)n * T * ld + h * HD;
-  load_tile(sK, base + D, ld, kb * BR, BR, T);
-  load_tile(sV, base + 2 * D, ld, kb * BR, BR, T);
   load_tile(sQ, base, ld, 0, Tp, T);
   load_tile(sdO, dctx + (long long)n * T * D + h * HD, D, 0, Tp, T);
   const float* lb = lse + ((long long)n * heads + h) * T;
   const float* db = delta + ((long long)n * heads + h) * T;
-  for (int i = threadIdx.x; i < Tp; i += ATT_THREADS) { s_lse[i] = i < T ? lb[i] : 0.f; s_dl[i] = i < T ? db[i] : 0.f; }
+  for (int i = threadIdx.x; i < Tp; i += blockDim.x) { s_lse[i] = i < T ? lb[i] : 0.f; s_dl[i] = i < T ? db[i] : 0.f; }
   cp_async_wait_all();
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  if (kb * BR + warp * 16 >= T) return;
+  for (int r0 = warp * 16; r0 < T; r0 += nwarps * 16) {
+  warp_stage_tile16(sK, base + D, ld, r0, T);
+  warp_stage_tile16(sV, base + 2 * D, ld, r0, T);
+  cp_async_wait_all();
+  __syncwarp();
   uint32_t ka[4][4], va[4][4];
-  load_a_frags(sK, warp * 16, ka);
-  load_a_frags(sV, warp * 16, va);
+  load_a_frags(sK, 0, ka);
+  load_a_frags(sV, 0, va);
   float dk[8][4], dv[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
@@ -339,7 +361,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const __nv_bf
       }
     }
   }
-  const int k0 = kb * BR + warp * 16 + g, k1 = k0 + 8;
+  const int k0 = r0 + g, k1 = k0 + 8;
   __nv_bfloat16* ob = dqkv + (long long)n * T * ld + h * HD;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
@@ -353,6 +375,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const __nv_bf
       *reinterpret_cast<uint32_t*>(ob + (long long)k1 * ld + 2 * D + d) = pack2(dv[nt][2], dv[nt][3]);
     }
   }
+  }  // tile loop
 }
 
 template <typename K>
@@ -363,16 +386,30 @@ int set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+// warps per CTA: fill ceil(T/16) row tiles with the fewest idle slots (ties -> more warps)
+static int pick_warps(int T) {
+  const int tiles = (T + 15) / 16;
+  int best = 4;
+  double best_eff = 0.0;
+  for (int w = 4; w <= MAX_WARPS; ++w) {
+    const int rounds = (tiles + w - 1) / w;
+    const double eff = (double)tiles / (double)(rounds * w);
+    if (eff >= best_eff - 1e-9) { best_eff = eff; best = w; }
+  }
+  return best;
+}
+
 extern "C" int cg_attention_fwd(const void* qkv, int Nimg, int T, int heads, void* ctx, float* lse, void* stream) {
   CG_REQUIRE(qkv && ctx && lse && Nimg > 0 && T > 0 && heads > 0, "cg_attention_fwd: bad arguments");
   const int Tp = (T + 63) & ~63;
   CG_REQUIRE(Tp <= 640, "cg_attention_fwd: T=%d exceeds the shared-memory resident limit (640)", T);
-  const size_t smem = (size_t)(BR + 2 * Tp) * 128;
+  const int W = pick_warps(T);
+  const size_t smem = (size_t)(2 * Tp) * 128 + (size_t)W * 2048;
   int rc = set_smem(attn_fwd_kernel, smem);
   if (rc) return rc;
   const float scale_log2 = 0.125f * LOG2E;  // 1/sqrt(64)
-  attn_fwd_kernel<<<dim3(Tp / BR, heads, Nimg), ATT_THREADS, smem, cg_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), T, heads, scale_log2,
-                                                                                      reinterpret_cast<__nv_bfloat16*>(ctx), lse);
+  attn_fwd_kernel<<<dim3(heads, Nimg), W * 32, smem, cg_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), T, heads, scale_log2,
+                                                                        reinterpret_cast<__nv_bfloat16*>(ctx), lse);
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -387,19 +424,18 @@ extern "C" int cg_attention_bwd(const void* qkv, const void* ctx, const void* dc
   attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(ctx), reinterpret_cast<const __nv_bfloat16*>(dctx), T, heads,
                                                                rows, delta_ws);
   CG_LAUNCH_CHECK();
-  const size_t smem_q = (size_t)(2 * BR + 2 * Tp) * 128;
+  const int W = pick_warps(T);
+  const size_t smem_q = (size_t)(2 * Tp) * 128 + (size_t)W * 4096;
   int rc = set_smem(attn_bwd_dq_kernel, smem_q);
   if (rc) return rc;
-  attn_bwd_dq_kernel<<<dim3(Tp / BR, heads, Nimg), ATT_THREADS, smem_q, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                                            reinterpret_cast<const __nv_bfloat16*>(dctx), lse, delta_ws, T, heads, 0.125f,
-                                                                            reinterpret_cast<__nv_bfloat16*>(dqkv));
+  attn_bwd_dq_kernel<<<dim3(heads, Nimg), W * 32, smem_q, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dctx), lse,
+                                                             delta_ws, T, heads, 0.125f, reinterpret_cast<__nv_bfloat16*>(dqkv));
   CG_LAUNCH_CHECK();
-  const size_t smem_kv = (size_t)(2 * BR + 2 * Tp) * 128 + 2 * sizeof(float) * Tp;
+  const size_t smem_kv = (size_t)(2 * Tp) * 128 + 2 * sizeof(float) * Tp + (size_t)W * 4096;
   rc = set_smem(attn_bwd_dkv_kernel, smem_kv);
   if (rc) return rc;
-  attn_bwd_dkv_kernel<<<dim3(Tp / BR, heads, Nimg), ATT_THREADS, smem_kv, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                                              reinterpret_cast<const __nv_bfloat16*>(dctx), lse, delta_ws, T, heads, 0.125f,
-                                                                              reinterpret_cast<__nv_bfloat16*>(dqkv));
+  attn_bwd_dkv_kernel<<<dim3(heads, Nimg), W * 32, smem_kv, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dctx), lse,
+                                                               delta_ws, T, heads, 0.125f, reinterpret_cast<__nv_bfloat16*>(dqkv));
   CG_LAUNCH_CHECK();
   return 0;
 }
