@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) attn_bwd_dq_kernel(const __nv_
 
 // dK, dV: CTA = 64 keys; Q, dO whole in smem (+ lse, delta).  Works on the transposed problem:
 // S^T = K Q^T, P^T = exp(S^T*scale - lse[q]);  dV = P^T dO;  dP^T = V dO^T;  dS^T = P^T*(dP^T - delta[q])*scale;  dK = dS^T Q.
-__global__ void __launch_bounds__(MAX_WARPS * 32) attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx,
+template <int MAXW, int MINB>
+__global__ void __launch_bounds__(MAXW * 32, MINB) attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx,
                                                                      const float* __restrict__ lse, const float* __restrict__ delta, int T, int heads,
                                                                      float scale, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -432,10 +433,19 @@ extern "C" int cg_attention_bwd(const void* qkv, const void* ctx, const void* dc
                                                              delta_ws, T, heads, 0.125f, reinterpret_cast<__nv_bfloat16*>(dqkv));
   CG_LAUNCH_CHECK();
   const size_t smem_kv = (size_t)(2 * Tp) * 128 + 2 * sizeof(float) * Tp + (size_t)W * 4096;
-  rc = set_smem(attn_bwd_dkv_kernel, smem_kv);
-  if (rc) return rc;
-  attn_bwd_dkv_kernel<<<dim3(heads, Nimg), W * 32, smem_kv, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dctx), lse,
-                                                               delta_ws, T, heads, 0.125f, reinterpret_cast<__nv_bfloat16*>(dqkv));
+  // <= 6 warps and <= 113 KB: cap registers so that two CTAs fit one SM (the kernel is latency bound)
+  if (W <= 6 && smem_kv <= 113 * 1024) {
+    rc = set_smem(attn_bwd_dkv_kernel<6, 2>, smem_kv);
+    if (rc) return rc;
+    attn_bwd_dkv_kernel<6, 2><<<dim3(heads, Nimg), W * 32, smem_kv, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dctx),
+                                                                       lse, delta_ws, T, heads, 0.125f, reinterpret_cast<__nv_bfloat16*>(dqkv));
+  } else {
+    rc = set_smem(attn_bwd_dkv_kernel<MAX_WARPS, 1>, smem_kv);
+    if (rc) return rc;
+    attn_bwd_dkv_kernel<MAX_WARPS, 1><<<dim3(heads, Nimg), W * 32, smem_kv, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                               reinterpret_cast<const __nv_bfloat16*>(dctx), lse, delta_ws, T, heads, 0.125f,
+                                                                               reinterpret_cast<__nv_bfloat16*>(dqkv));
+  }
   CG_LAUNCH_CHECK();
   return 0;
 }
