@@ -45,6 +45,7 @@ def parse_args():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--two-forwards", action="store_true", help="evaluate the UNet separately for the sampler and for cond_fn like the reference does")
     p.add_argument("--cpu-budget-s", type=float, default=240.0)
     return p.parse_args()
 
@@ -219,9 +220,7 @@ def main():
             if world > 1:
                 dist.all_reduce(gbuf)
             return {"sample": x, "pred_xstart": gbuf.unsqueeze(0)}
-        guidance.current_timestep = i
-        t = torch.full((1,), i, device=dev, dtype=torch.long)
-        return diffusion.ddim_sample(unet, x, t, clip_denoised=False, cond_fn=guidance.cond_fn, model_kwargs={})
+        return guidance.ddim_step(x, i, reuse_forward=not args.two_forwards)
 
     def barrier():
         if world > 1:
@@ -293,7 +292,7 @@ def main():
     line = {
         "metric": "CLIP-guided DDIM steps/s @%dx%d" % (size, size), "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": desc, "cutouts_per_step": cuts_per_step, "cutouts_per_rank": -(-cuts_per_step // world), "unet": "fp16 stock PyTorch, replicated",
+        "config": {"workload": desc, "cutouts_per_step": cuts_per_step, "cutouts_per_rank": -(-cuts_per_step // world), "unet": "fp16 stock PyTorch, replicated; %s" % ("two forwards per step (sampler + cond_fn) like the reference" if args.two_forwards else "one grad-enabled forward shared by sampler and cond_fn (identical results)"),
                    "clip": "bf16 operands / fp32 accumulate + fp32 residual stream, random init", "parallelism": "cutouts sharded x%d, 1 all-reduce/step" % world,
                    "l2": "working set (1.1 GB UNet + ViT weights + activations) far exceeds the 126 MB L2; no flush"},
         "cutouts_per_s": cuts_per_step * value,

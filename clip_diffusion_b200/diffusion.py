@@ -91,9 +91,22 @@ class SpacedDiffusion:
         out["mean"] = _extract(self.posterior_mean_coef1, t, x) * out["pred_xstart"] + _extract(self.posterior_mean_coef2, t, x) * x
         return out
 
+    def finish_p_mean_variance(self, x, t, pred_xstart_raw, clip_denoised=False, denoised_fn=None):
+        """The sampler-side post-processing of p_mean_variance on an already computed raw x0 prediction (used when one
+        grad-enabled UNet forward serves both the sampler and cond_fn)."""
+        pred_xstart = pred_xstart_raw
+        if denoised_fn is not None:
+            pred_xstart = denoised_fn(pred_xstart)
+        if clip_denoised:
+            pred_xstart = pred_xstart.clamp(-1, 1)
+        mean = _extract(self.posterior_mean_coef1, t, x) * pred_xstart + _extract(self.posterior_mean_coef2, t, x) * x
+        return {"mean": mean, "pred_xstart": pred_xstart}
+
     @torch.no_grad()
-    def ddim_sample(self, model, x, t, clip_denoised=False, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0, noise=None):
-        out_orig = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn, model_kwargs=model_kwargs)
+    def ddim_sample(self, model, x, t, clip_denoised=False, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0, noise=None,
+                    out_orig=None):
+        if out_orig is None:
+            out_orig = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn, model_kwargs=model_kwargs)
         out = self.condition_score(cond_fn, out_orig, x, t, model_kwargs=model_kwargs) if cond_fn is not None else out_orig
         eps = self._eps_from_xstart(x, t, out["pred_xstart"])
         alpha_bar = _extract(self.alphas_cumprod, t, x)

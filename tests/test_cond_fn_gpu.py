@@ -151,3 +151,36 @@ def test_nan_guard_returns_zeros():
     step.current_timestep = 5
     out = step.cond_fn(s["x"].cuda(), s["diffusion"].model_timesteps(torch.tensor([5], device="cuda")))
     assert (out == 0).all()  # sample.py:228-233
+
+
+def test_ddim_step_forward_reuse_is_identical():
+    """One shared grad-enabled UNet forward gives the same DDIM step as the reference's two forwards."""
+    from clip_diffusion_b200.sample import GuidanceStep
+
+    s = _setup()
+    outs = []
+    for reuse in (False, True):
+        step = GuidanceStep(s["diffusion"], s["unet_gpu"], s["mine"], s["text_gpu"], config=s["cfg"], record_source=s["record_source"])
+        outs.append(step.ddim_step(s["x"].cuda(), 30, reuse_forward=reuse))
+    for k in ("sample", "pred_xstart"):
+        assert (outs[0][k] - outs[1][k]).abs().max().item() <= 1e-5 * max(1.0, outs[0][k].abs().max().item())
+
+
+def test_fast_groupnorm_matches_groupnorm32():
+    """unet.GroupNorm32's CUDA/fp16 path (split statistics, stock torch ops) == guided-diffusion's fp32 GroupNorm, fwd + bwd."""
+    from clip_diffusion_b200.unet import GroupNorm32
+
+    torch.manual_seed(0)
+    for shape in [(1, 128, 64, 64), (2, 256, 16, 16), (1, 512, 8 * 8)]:
+        gn = GroupNorm32(32, shape[1]).cuda()
+        with torch.no_grad():
+            gn.weight.normal_(1, 0.1); gn.bias.normal_(0, 0.1)
+        x = (torch.randn(shape, device="cuda") * 2 + 0.3).half().requires_grad_()
+        dy = torch.randn(shape, device="cuda").half()
+        y = gn(x)
+        (g,) = torch.autograd.grad((y.float() * dy.float()).sum(), x)
+        xr = x.detach().float().requires_grad_()
+        yr = torch.nn.functional.group_norm(xr, 32, gn.weight, gn.bias, gn.eps)
+        (gr,) = torch.autograd.grad((yr * dy.float()).sum(), xr)
+        assert (y.float() - yr).abs().max().item() < 2e-2
+        assert ((g.float() - gr).norm() / gr.norm()).item() < 5e-3
