@@ -45,6 +45,7 @@ def parse_args():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-graphs", action="store_true", help="do not capture the replicated UNet forward/backward into CUDA graphs")
     p.add_argument("--two-forwards", action="store_true", help="evaluate the UNet separately for the sampler and for cond_fn like the reference does")
     p.add_argument("--cpu-budget-s", type=float, default=240.0)
     return p.parse_args()
@@ -202,6 +203,17 @@ def main():
     clip_only = args.workload == "clip-only"
     unet = None if clip_only else create_unet(size if size in (256, 512) else 512, seed=2, device=dev, use_fp16=True)
     diffusion = SpacedDiffusion(steps=ddim)
+    unet_graphed = False
+    if unet is not None and not args.no_graphs and not args.two_forwards:
+        # The replicated UNet is ~7k tiny stock-PyTorch launches per step and the step was launch-bound on the host
+        # (profiles/r01_*): capture its forward and backward once into CUDA graphs (static shapes, batch 1).
+        sx = torch.randn(1, 3, size, size, device=dev, requires_grad=True)
+        st = torch.full((1,), 500.0, device=dev)
+        graphed = torch.cuda.make_graphed_callables(unet, (sx, st))
+        unet_module = unet
+        unet = lambda x, t, y=None: graphed(x, t)  # noqa: E731  (same call signature as the module)
+        unet_graphed = True
+        del sx, st
     clip_models = load_clip_models(names, dev)
     g = torch.Generator().manual_seed(0)
     text = {n: {"embeddings": torch.randn(1, m.visual.output_dim, generator=g).to(dev), "weights": torch.tensor(1.0, device=dev)} for n, m in clip_models.items()}
@@ -292,7 +304,7 @@ def main():
     line = {
         "metric": "CLIP-guided DDIM steps/s @%dx%d" % (size, size), "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": desc, "cutouts_per_step": cuts_per_step, "cutouts_per_rank": -(-cuts_per_step // world), "unet": "fp16 stock PyTorch, replicated; %s" % ("two forwards per step (sampler + cond_fn) like the reference" if args.two_forwards else "one grad-enabled forward shared by sampler and cond_fn (identical results)"),
+        "config": {"workload": desc, "cutouts_per_step": cuts_per_step, "cutouts_per_rank": -(-cuts_per_step // world), "unet_cuda_graphs": unet_graphed, "unet": "fp16 stock PyTorch, replicated; %s" % ("two forwards per step (sampler + cond_fn) like the reference" if args.two_forwards else "one grad-enabled forward shared by sampler and cond_fn (identical results)"),
                    "clip": "bf16 operands / fp32 accumulate + fp32 residual stream, random init", "parallelism": "cutouts sharded x%d, 1 all-reduce/step" % world,
                    "l2": "working set (1.1 GB UNet + ViT weights + activations) far exceeds the 126 MB L2; no flush"},
         "cutouts_per_s": cuts_per_step * value,
