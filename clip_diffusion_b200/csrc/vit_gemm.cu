@@ -15,6 +15,7 @@
 // Weights are frozen (models.py:71), so every GEMM of the backward pass is a dgrad with a pre-transposed
 // weight copy: all calls have both operands K-major and share this one kernel.
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 #include "common.cuh"
@@ -321,6 +322,177 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tn_kernel(const __gr
   }
 }
 
+// ---------------------------------------------------------------------------------- CTA-pair variant
+// cta_group::2: two CTAs of one cluster (one TPC) share a 256x256 output tile.  Each CTA stages ITS 128 rows of A and
+// HALF of the B tile (128 of the 256 output columns); the leader CTA issues tcgen05.mma.cta_group::2 (M=256), which
+// reads both halves of B from both SMs' shared memory, so per 64-deep k-block the pair pulls 64 KB from L2 instead of
+// 2 x 48 KB -- the single-CTA kernel is L2->smem bound at ~1.0-1.15 PFLOP/s (profiles/).  6-stage ring (32 KB/stage).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(leader_bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+constexpr int STAGES2 = 6;
+constexpr int BN2 = 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+    gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = BM * BK * 2;         // this CTA's 128 rows of A
+  constexpr uint32_t B_BYTES = (BN2 / 2) * BK * 2;  // this CTA's half of the B tile
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN2;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES2 * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES2 + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES2 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES2 + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES2 + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_tiles = (g.M + 2 * BM - 1) / (2 * BM), n_tiles = g.N / BN2;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = g.K / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * NUM_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs): data into OWN smem, bytes reported to the LEADER's full barrier
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
+        const int m0 = m_blk * 2 * BM + (int)rank * BM;
+        const int n0 = n_blk * BN2 + (int)rank * (BN2 / 2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+          const uint32_t lead_bar = map_to_cta(full_bar(stage), 0);
+          tma_load_2d_pair(a_dst, &tmA, lead_bar, kb * BK, m0);
+          tma_load_2d_pair(b_dst, &tmB, lead_bar, kb * BK, n0);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + stage * STAGE_BYTES, b_addr = a_addr + A_BYTES;
+          const uint64_t adesc = make_smem_desc(a_addr), bdesc = make_smem_desc(b_addr);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(empty_bar(stage));  // frees the slot in BOTH CTAs
+          if (kb == k_blocks - 1) umma_commit_pair(tfull_bar(as));
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    const int chalf = (warp - 4) >> 2;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tfull_bar(as), aphase);
+      tcgen05_fence_after();
+      const long long row = (long long)m_blk * 2 * BM + (long long)rank * BM + q * 32 + lane;
+      long long orow = row;
+      if (EPI == CG_EPI_PATCH_POS_F32) orow = (row / g.g2) * (g.g2 + 1) + 1 + row % g.g2;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN2);
+#pragma unroll 1
+      for (int c = chalf * (BN2 / 2); c < (chalf + 1) * (BN2 / 2); c += 32) {
+        uint32_t acc[32];
+        tmem_ld32(t_row + (uint32_t)c, acc);
+        tmem_ld_wait();
+        if (row < g.M) epilogue_chunk<EPI>(g, row, orow, n_blk * BN2 + c, acc);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(map_to_cta(tempty_bar(as), 0));
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still read this CTA's shared memory
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -418,6 +590,46 @@ int dispatch(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
   return CG_EINVAL;
 }
 
+template <int EPI>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES2 * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    CG_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN2);
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = tiles;
+  gemm_bf16_tn_pair_kernel<EPI><<<2 * clusters, NUM_THREADS, smem, s>>>(ta, tb, g);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int dispatch_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t s) {
+  switch (epi) {
+    case CG_EPI_BIAS_BF16: return launch_pair<CG_EPI_BIAS_BF16>(ta, tb, g, s);
+    case CG_EPI_BIAS_RESID_F32: return launch_pair<CG_EPI_BIAS_RESID_F32>(ta, tb, g, s);
+    case CG_EPI_BIAS_QGELU_BF16: return launch_pair<CG_EPI_BIAS_QGELU_BF16>(ta, tb, g, s);
+    case CG_EPI_DQGELU_BF16: return launch_pair<CG_EPI_DQGELU_BF16>(ta, tb, g, s);
+    case CG_EPI_F32: return launch_pair<CG_EPI_F32>(ta, tb, g, s);
+    case CG_EPI_BF16: return launch_pair<CG_EPI_BF16>(ta, tb, g, s);
+    case CG_EPI_PATCH_POS_F32: return launch_pair<CG_EPI_PATCH_POS_F32>(ta, tb, g, s);
+  }
+  cg_set_error("cg_gemm_bf16_tn: unknown epilogue %d", epi);
+  return CG_EINVAL;
+}
+
+// CTA-pair kernel on/off: CG_GEMM_PAIR=0/1 (default set below once validated on hardware)
+bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CG_GEMM_PAIR");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v != 0;
+}
+
 }  // namespace
 
 extern "C" int cg_gemm_bf16_tn(const void* A, const void* B, int M, int N, int K, int64_t lda, int64_t ldb, int epilogue, const float* bias,
@@ -437,6 +649,12 @@ extern "C" int cg_gemm_bf16_tn(const void* A, const void* B, int M, int N, int K
   CUtensorMap ta, tb;
   int rc = make_tensor_map(&ta, A, M, K, lda, BM);
   if (rc) return rc;
+  if (bn == 256 && M > 2 * BM && use_pair_kernel()) {
+    rc = make_tensor_map(&tb, B, N, K, ldb, BN2 / 2);
+    if (rc) return rc;
+    GemmArgs gp = {M, N, K, bias, out, aux, (long long)ldo, pos, g2};
+    return dispatch_pair(epilogue, ta, tb, gp, cg_stream(stream));
+  }
   rc = make_tensor_map(&tb, B, N, K, ldb, bn);
   if (rc) return rc;
   GemmArgs g = {M, N, K, bias, out, aux, (long long)ldo, pos, g2};
