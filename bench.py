@@ -298,6 +298,11 @@ def main():
             dist.destroy_process_group()
         return
     tf_peak, hbm_peak, peak_src = measured_peaks()
+    traffic = None  # dram bytes per GEMM launch from the committed ncu capture of this same command (profiles/)
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic_%s.json" % args.workload)
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("avg_dram_bytes_per_launch")
     value = K / (ms / 1e3)
     e2e = K / (ms_e2e / 1e3)
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
@@ -312,7 +317,8 @@ def main():
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM/TMA, all ViT GEMMs)", "achieved": achieved, "peak": tf_peak,
-                     "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None, "peak_source": peak_src, "launches": len(prof),
+                     "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
+                     "algorithmic_flops_per_launch": gemm_flops / max(len(prof), 1), "peak_source": peak_src, "launches": len(prof),
                      "share_of_step": gemm_ms / ms if ms > 0 else None},
     }
     if world == 1 and not args.no_cpu_baseline and not clip_only:

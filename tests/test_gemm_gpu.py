@@ -97,3 +97,39 @@ def test_gemm_rejects_bad_shapes():
     b = torch.zeros(128, 48, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(_lib.ClipGuideError):
         ops.gemm_bf16_tn(a, b, _lib.EPI_F32)
+
+
+def test_gemm_cta_pair_kernel_in_subprocess():
+    """The cta_group::2 (CTA-pair, 256x256 tile) variant is selected with CG_GEMM_PAIR=1 at library load; run the same
+    parity cases in a child process with that environment (and a timeout: a cluster deadlock must not hang the suite)."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from clip_diffusion_b200 import _lib, vit_ops
+torch.manual_seed(0)
+worst = 0.0
+for (M, N, K) in [(300, 256, 64), (1576, 2304, 768), (6304, 768, 3072), (16448, 1024, 640), (777, 512, 1024), (257, 256, 128)]:
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    b = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda") * 0.1
+    ref = a.float() @ b.float().t()
+    out = vit_ops.gemm_bf16_tn(a, b, _lib.EPI_F32)
+    worst = max(worst, ((out - ref).abs().max() / ref.abs().max().clamp_min(1)).item())
+    h, u = vit_ops.gemm_bf16_tn(a, b, _lib.EPI_BIAS_QGELU_BF16, bias=bias)
+    pre = ref + bias
+    worst = max(worst, ((u.float() - pre).abs().max() / pre.abs().max().clamp_min(1)).item() / 20)
+    r0 = torch.randn(M, N, device="cuda")
+    o2 = vit_ops.gemm_bf16_tn(a, b, _lib.EPI_BIAS_RESID_F32, bias=bias, aux=r0)
+    worst = max(worst, ((o2 - (r0 + pre)).abs().max() / pre.abs().max().clamp_min(1)).item())
+torch.cuda.synchronize()
+print("WORST", worst)
+assert worst < 1e-3, worst
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CG_GEMM_PAIR="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "WORST" in res.stdout
