@@ -620,14 +620,26 @@ int dispatch_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const G
   return CG_EINVAL;
 }
 
-// CTA-pair kernel on/off: CG_GEMM_PAIR=0/1 (default set below once validated on hardware)
-bool use_pair_kernel() {
-  static int v = -1;
-  if (v < 0) {
+// CTA-pair kernel selection.  CG_GEMM_PAIR=0 never, =1 whenever eligible, unset = heuristic from the B200 measurements in
+// profiles/ (ViT-L/14 x 64: pair is +16% on K=4096 fp32-out GEMMs, +3..7% on bias/bf16 epilogues, -2% on the QuickGELU
+// epilogues which are epilogue-bound; and 256x256 tiles lose when they quantise badly, e.g. 75 tiles on 74 clusters).
+int pair_mode() {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("CG_GEMM_PAIR");
-    v = e ? (atoi(e) != 0) : 0;
+    v = e ? (atoi(e) != 0 ? 1 : 0) : -1;
   }
-  return v != 0;
+  return v;
+}
+bool use_pair_kernel(int M, int N, int K, int epilogue) {
+  const int mode = pair_mode();
+  if (mode >= 0) return mode == 1;
+  if (epilogue == CG_EPI_BIAS_QGELU_BF16 || epilogue == CG_EPI_DQGELU_BF16 || K < 1024) return false;
+  const int sms = num_sms();
+  const long long t1 = (long long)((M + BM - 1) / BM) * (N / 256), t2 = (long long)((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
+  const double eff1 = (double)t1 / (double)(((t1 + sms - 1) / sms) * sms);
+  const double eff2 = (double)t2 / (double)(((t2 + sms / 2 - 1) / (sms / 2)) * (sms / 2));
+  return eff2 * 1.10 > eff1;
 }
 
 }  // namespace
@@ -649,7 +661,7 @@ extern "C" int cg_gemm_bf16_tn(const void* A, const void* B, int M, int N, int K
   CUtensorMap ta, tb;
   int rc = make_tensor_map(&ta, A, M, K, lda, BM);
   if (rc) return rc;
-  if (bn == 256 && M > 2 * BM && use_pair_kernel()) {
+  if (bn == 256 && M > 2 * BM && use_pair_kernel(M, N, K, epilogue)) {
     rc = make_tensor_map(&tb, B, N, K, ldb, BN2 / 2);
     if (rc) return rc;
     GemmArgs gp = {M, N, K, bias, out, aux, (long long)ldo, pos, g2};
