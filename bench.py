@@ -136,10 +136,14 @@ def build_cpu_reference(wl, seed=0):
     cond_fn = make_conditon_function(diffusion, unet, clip, text, lambda: state["ct"], cfg, record_source)
     x = torch.randn(1, 3, size, size, generator=g)
 
+    def denoised_fn(x_start):  # sample.py:116-132
+        thr = torch.quantile(x_start.reshape(x_start.shape[0], -1).abs(), 0.995, dim=-1).clamp(min=1.0).view(-1, 1, 1, 1)
+        return x_start.clamp(min=-thr, max=thr) / thr
+
     def step(x, i):
         state["ct"] = i
         t = torch.full((1,), i, dtype=torch.long)
-        return diffusion.ddim_sample(unet, x, t, clip_denoised=False, cond_fn=cond_fn, model_kwargs={})["sample"]
+        return diffusion.ddim_sample(unet, x, t, clip_denoised=False, denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs={}, eta=0.8)["sample"]
 
     return step, x, ddim, (n_over + n_inner) * batches * len(names)
 
@@ -188,7 +192,7 @@ def main():
     from clip_diffusion_b200 import _lib, vit_ops
     from clip_diffusion_b200.diffusion import SpacedDiffusion
     from clip_diffusion_b200.models import load_clip_models
-    from clip_diffusion_b200.sample import GuidanceStep
+    from clip_diffusion_b200.sample import GuidanceStep, make_denoised_function
     from clip_diffusion_b200.unet import create_unet
     from clip_diffusion_b200.utils.functional import set_seed
 
@@ -219,6 +223,7 @@ def main():
     text = {n: {"embeddings": torch.randn(1, m.visual.output_dim, generator=g).to(dev), "weights": torch.tensor(1.0, device=dev)} for n, m in clip_models.items()}
     guidance = GuidanceStep(diffusion, unet, clip_models, text, config=cfg, rank=rank, world_size=world,
                             range_scale=150.0 if args.workload == "c3" else 0.0)
+    denoised_fn = make_denoised_function(0.995)  # reference defaults: dynamic thresholding 0.995, eta 0.8 (sample.py:66-71)
     cuts_per_step = (n_over + n_inner) * batches * len(names)
     x_host = torch.randn(1, 3, size, size, generator=g).pin_memory()
     out_host = torch.empty(2, 3, size, size).pin_memory()
@@ -232,7 +237,7 @@ def main():
             if world > 1:
                 dist.all_reduce(gbuf)
             return {"sample": x, "pred_xstart": gbuf.unsqueeze(0)}
-        return guidance.ddim_step(x, i, reuse_forward=not args.two_forwards)
+        return guidance.ddim_step(x, i, eta=0.8, denoised_fn=denoised_fn, reuse_forward=not args.two_forwards)
 
     def barrier():
         if world > 1:

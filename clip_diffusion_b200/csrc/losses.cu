@@ -5,7 +5,9 @@
 namespace {
 
 // ---- total variation (losses.py:20-28) ---------------------------------------------------------
-// One thread per 4 consecutive pixels of a row; neighbours via direct (cached) loads.
+// One thread per 4 consecutive pixels of a row.  VEC path (W % 4 == 0, 16-byte aligned): three 128-bit loads (row
+// above / this row / row below) + two scalar halo loads per 4 outputs; neighbours come from L1/L2, HBM sees each pixel once.
+template <bool VEC>
 __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, int C, int H, int W, float gscale,
                                                  int accumulate, float* __restrict__ loss, float* __restrict__ grad) {
   __shared__ float red[32];
@@ -25,19 +27,30 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, in
     const int h = (int)(row % H);
     const int x0 = xv << 2;
     const float* r = xb + row * W;
-    float cur[6];  // x[x0-1 .. x0+4]
+    float cur[6], up[4], dn[4];  // cur = x[x0-1 .. x0+4]
+    if (VEC) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(r + x0));
+      cur[1] = c4.x; cur[2] = c4.y; cur[3] = c4.z; cur[4] = c4.w;
+      cur[0] = x0 > 0 ? __ldg(r + x0 - 1) : 0.f;
+      cur[5] = x0 + 4 < W ? __ldg(r + x0 + 4) : 0.f;
+      float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = u4;
+      if (h > 0) u4 = __ldg(reinterpret_cast<const float4*>(r - W + x0));
+      if (h + 1 < H) d4 = __ldg(reinterpret_cast<const float4*>(r + W + x0));
+      up[0] = u4.x; up[1] = u4.y; up[2] = u4.z; up[3] = u4.w;
+      dn[0] = d4.x; dn[1] = d4.y; dn[2] = d4.z; dn[3] = d4.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int xx = x0 - 1 + i;
-      cur[i] = (xx >= 0 && xx < W) ? __ldg(r + xx) : 0.f;
-    }
-    float up[4], dn[4];
+      for (int i = 0; i < 6; ++i) {
+        const int xx = x0 - 1 + i;
+        cur[i] = (xx >= 0 && xx < W) ? __ldg(r + xx) : 0.f;
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int xx = x0 + i;
-      const bool ok = xx < W;
-      up[i] = (ok && h > 0) ? __ldg(r - W + xx) : 0.f;
-      dn[i] = (ok && h + 1 < H) ? __ldg(r + W + xx) : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const int xx = x0 + i;
+        const bool ok = xx < W;
+        up[i] = (ok && h > 0) ? __ldg(r - W + xx) : 0.f;
+        dn[i] = (ok && h + 1 < H) ? __ldg(r + W + xx) : 0.f;
+      }
     }
     float g[4];
 #pragma unroll
@@ -54,7 +67,7 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, in
     }
     if (gb) {
       float* o = gb + row * W + x0;
-      if (x0 + 3 < W && ((W & 3) == 0)) {
+      if (VEC) {
         float4 w = make_float4(g[0], g[1], g[2], g[3]);
         if (accumulate) { const float4 p = *reinterpret_cast<float4*>(o); w.x += p.x; w.y += p.y; w.z += p.z; w.w += p.w; }
         *reinterpret_cast<float4*>(o) = w;
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(128) sph_bwd_kernel(const float* __restrict__ 
 
 static int grid_for(int64_t work_items, int threads) {
   int64_t blocks = (work_items + threads - 1) / threads;
-  const int64_t cap = (int64_t)CG_NUM_SMS * 8;
+  const int64_t cap = (int64_t)CG_NUM_SMS * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -206,7 +219,9 @@ extern "C" int cg_tv_loss_fwd_bwd(const float* x, int B, int C, int H, int W, fl
   if (loss) CG_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * B, s));
   const int64_t nvec = (int64_t)C * H * ((W + 3) / 4);
   dim3 grid(grid_for(nvec, 256), B);
-  tv_kernel<<<grid, 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad);
+  const bool vec = (W % 4 == 0) && (((uintptr_t)x | (uintptr_t)grad) & 15) == 0;
+  if (vec) tv_kernel<true><<<grid, 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad);
+  else tv_kernel<false><<<grid, 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad);
   CG_LAUNCH_CHECK();
   return 0;
 }

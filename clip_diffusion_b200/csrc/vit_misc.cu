@@ -13,7 +13,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// one warp per row; D % 128 == 0 (each lane owns D/32 values as float4 groups strided by 32 lanes)
+// one warp per row; D = 128*NV (each lane owns NV float4 groups strided by 32 lanes, fully unrolled in registers)
+template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      int M, int D, long long row_stride, __nv_bfloat16* __restrict__ yb, float* __restrict__ yf,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
@@ -21,29 +22,25 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * row_stride);
-  const int nv = D >> 7;  // float4 per lane
-  float4 v[LN_MAX_PER_LANE / 4];
+  float4 v[NV];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i)
-    if (i < nv) { v[i] = xr[i * 32 + lane]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  for (int i = 0; i < NV; ++i) { v[i] = xr[i * 32 + lane]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
   s = warp_sum(s);
   const float mean = s / (float)D;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i)
-    if (i < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += a * a + b * b + c * c + d * d;
-    }
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
   q = warp_sum(q);
   const float rstd = rsqrtf(q / (float)D + LN_EPS);
   if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i)
-    if (i < nv) {
+  for (int i = 0; i < NV; ++i) {
       const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
       float4 y;
       y.x = (v[i].x - mean) * rstd * g.x + b.x; y.y = (v[i].y - mean) * rstd * g.y + b.y;
@@ -53,6 +50,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int M, int D,
                                                      long long row_stride, int accumulate, float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb) {
@@ -62,13 +60,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * row_stride);
   const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)row * D);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const int nv = D >> 7;
   const float mean = mean_in[row], rstd = rstd_in[row];
-  float4 xh[LN_MAX_PER_LANE / 4], dh[LN_MAX_PER_LANE / 4];
+  float4 xh[NV], dh[NV];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i)
-    if (i < nv) {
+  for (int i = 0; i < NV; ++i) {
       const float4 xv = xr[i * 32 + lane], d = dyr[i * 32 + lane], g = __ldg(g4 + i * 32 + lane);
       xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
       dh[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
@@ -79,8 +75,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   s2 = warp_sum(s2) / (float)D;
   float4* dxr = reinterpret_cast<float4*>(dx + (long long)row * row_stride);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i)
-    if (i < nv) {
+  for (int i = 0; i < NV; ++i) {
       float4 r;
       r.x = rstd * (dh[i].x - s1 - xh[i].x * s2); r.y = rstd * (dh[i].y - s1 - xh[i].y * s2);
       r.z = rstd * (dh[i].z - s1 - xh[i].z * s2); r.w = rstd * (dh[i].w - s1 - xh[i].w * s2);
@@ -174,7 +169,13 @@ extern "C" int cg_layernorm_fwd(const float* x, const float* gamma, const float*
   CG_REQUIRE(x && gamma && beta && mean && rstd && (y_bf16 || y_f32), "cg_layernorm_fwd: null pointer");
   CG_REQUIRE(M > 0 && D > 0 && D % 128 == 0 && D / 32 <= LN_MAX_PER_LANE, "cg_layernorm_fwd: D=%d must be a multiple of 128 and <= %d", D, 32 * LN_MAX_PER_LANE);
   CG_REQUIRE(row_stride >= D && row_stride % 4 == 0, "cg_layernorm_fwd: bad row stride");
-  ln_fwd_kernel<<<rows_grid(M), 256, 0, cg_stream(stream)>>>(x, gamma, beta, M, D, row_stride, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd);
+#define CG_LN_FWD(NV) \
+  case NV: ln_fwd_kernel<NV><<<rows_grid(M), 256, 0, cg_stream(stream)>>>(x, gamma, beta, M, D, row_stride, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd); break;
+  switch (D / 128) {
+    CG_LN_FWD(1) CG_LN_FWD(2) CG_LN_FWD(3) CG_LN_FWD(4) CG_LN_FWD(5) CG_LN_FWD(6) CG_LN_FWD(7) CG_LN_FWD(8) CG_LN_FWD(9) CG_LN_FWD(10)
+    default: cg_set_error("cg_layernorm_fwd: unsupported D=%d", D); return CG_EINVAL;
+  }
+#undef CG_LN_FWD
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -184,8 +185,13 @@ extern "C" int cg_layernorm_bwd(const float* dy, const float* x, const float* ga
   CG_REQUIRE(dy && x && gamma && mean && rstd && dx, "cg_layernorm_bwd: null pointer");
   CG_REQUIRE(M > 0 && D > 0 && D % 128 == 0 && D / 32 <= LN_MAX_PER_LANE, "cg_layernorm_bwd: D=%d must be a multiple of 128 and <= %d", D, 32 * LN_MAX_PER_LANE);
   CG_REQUIRE(row_stride >= D && row_stride % 4 == 0, "cg_layernorm_bwd: bad row stride");
-  ln_bwd_kernel<<<rows_grid(M), 256, 0, cg_stream(stream)>>>(dy, x, gamma, mean, rstd, M, D, row_stride, accumulate, dx,
-                                                            reinterpret_cast<__nv_bfloat16*>(dx_bf16));
+#define CG_LN_BWD(NV) \
+  case NV: ln_bwd_kernel<NV><<<rows_grid(M), 256, 0, cg_stream(stream)>>>(dy, x, gamma, mean, rstd, M, D, row_stride, accumulate, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16)); break;
+  switch (D / 128) {
+    CG_LN_BWD(1) CG_LN_BWD(2) CG_LN_BWD(3) CG_LN_BWD(4) CG_LN_BWD(5) CG_LN_BWD(6) CG_LN_BWD(7) CG_LN_BWD(8) CG_LN_BWD(9) CG_LN_BWD(10)
+    default: cg_set_error("cg_layernorm_bwd: unsupported D=%d", D); return CG_EINVAL;
+  }
+#undef CG_LN_BWD
   CG_LAUNCH_CHECK();
   return 0;
 }

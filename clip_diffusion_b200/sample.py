@@ -82,6 +82,19 @@ def make_conditon_function(diffusion, model, clip_models, text_embeddings_and_we
     return conditon_function
 
 
+def make_denoised_function(dynamic_thresholding_percentile=0.995):
+    """Imagen-style dynamic thresholding applied to the sampler's x0 prediction (sample.py:116-132): clamp to the
+    per-sample |x| quantile (at least 1) and rescale.  Plain torch ops (a selection kernel is the
+    next widening step); part of the benchmarked step because the reference passes it as ``denoised_fn`` (sample.py:254,268)."""
+
+    def denoised_function(x_start):
+        threshold = torch.quantile(x_start.reshape(x_start.shape[0], -1).abs().float(), dynamic_thresholding_percentile, dim=-1)
+        threshold = threshold.clamp(min=1.0).view(-1, *((1,) * (x_start.ndim - 1))).to(x_start.dtype)
+        return x_start.clamp(min=-threshold, max=threshold) / threshold
+
+    return denoised_function
+
+
 def shard_range(n, rank, world_size):
     """Contiguous slice [start, stop) of n cutouts owned by ``rank``; sizes differ by at most one."""
     base, rem = divmod(n, world_size)
