@@ -84,6 +84,61 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, in
   }
 }
 
+// 2-D tiled variant (W % 128 == 0): a block owns a 32-row x 128-column tile of one plane; warp w walks rows w, w+8, ...
+// so the rows above/below a warp's row are the rows its neighbour warps load at the same time (L1 hits) -- the row-major
+// grid-stride kernel above re-read every row three times from L2 and stalled at ~50% of HBM peak.
+__global__ void __launch_bounds__(256) tv_tiled_kernel(const float* __restrict__ x, int C, int H, int W, float gscale, int accumulate,
+                                                       float* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ float red[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int plane_id = blockIdx.z;  // b*C + c
+  const int b = plane_id / C;
+  const int64_t per_img = (int64_t)C * H * W;
+  const float inv = 1.0f / (float)per_img;
+  const float gs = 2.0f * gscale * inv;
+  const float* xp = x + (int64_t)plane_id * H * W;
+  float* gp = grad ? grad + (int64_t)plane_id * H * W : nullptr;
+  const int x0 = blockIdx.x * 128 + lane * 4;
+  const int h0 = blockIdx.y * 32;
+  float acc = 0.f;
+#pragma unroll 1
+  for (int r = warp; r < 32; r += 8) {
+    const int h = h0 + r;
+    if (h >= H) break;
+    const float* row = xp + (int64_t)h * W;
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(row + x0));
+    const float left = x0 > 0 ? __ldg(row + x0 - 1) : 0.f;
+    const float right = x0 + 4 < W ? __ldg(row + x0 + 4) : 0.f;
+    float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = u4;
+    if (h > 0) u4 = __ldg(reinterpret_cast<const float4*>(row - W + x0));
+    if (h + 1 < H) d4 = __ldg(reinterpret_cast<const float4*>(row + W + x0));
+    const float cur[6] = {left, c4.x, c4.y, c4.z, c4.w, right};
+    const float up[4] = {u4.x, u4.y, u4.z, u4.w}, dn[4] = {d4.x, d4.y, d4.z, d4.w};
+    float g[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xx = x0 + i;
+      const float c = cur[i + 1];
+      const float dx = (xx + 1 < W) ? cur[i + 2] - c : 0.f;
+      const float dy = (h + 1 < H) ? dn[i] - c : 0.f;
+      const float dxl = (xx > 0) ? c - cur[i] : 0.f;
+      const float dyu = (h > 0) ? c - up[i] : 0.f;
+      acc += dx * dx + dy * dy;
+      g[i] = gs * (dxl + dyu - dx - dy);
+    }
+    if (gp) {
+      float4* o = reinterpret_cast<float4*>(gp + (int64_t)h * W + x0);
+      float4 w = make_float4(g[0], g[1], g[2], g[3]);
+      if (accumulate) { const float4 p = *o; w.x += p.x; w.y += p.y; w.z += p.z; w.w += p.w; }
+      *o = w;
+    }
+  }
+  if (loss) {
+    const float t = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(loss + b, t * inv);
+  }
+}
+
 // ---- rgb range (losses.py:31-35) -----------------------------------------------------------------
 __global__ void __launch_bounds__(256) range_kernel(const float* __restrict__ x, int64_t per_img, float gscale, int accumulate,
                                                     float* __restrict__ loss, float* __restrict__ grad) {
@@ -220,6 +275,11 @@ extern "C" int cg_tv_loss_fwd_bwd(const float* x, int B, int C, int H, int W, fl
   const int64_t nvec = (int64_t)C * H * ((W + 3) / 4);
   dim3 grid(grid_for(nvec, 256), B);
   const bool vec = (W % 4 == 0) && (((uintptr_t)x | (uintptr_t)grad) & 15) == 0;
+  if (vec && W % 128 == 0 && (long long)B * C <= 65535) {
+    tv_tiled_kernel<<<dim3(W / 128, (H + 31) / 32, B * C), 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad);
+    CG_LAUNCH_CHECK();
+    return 0;
+  }
   if (vec) tv_kernel<true><<<grid, 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad);
   else tv_kernel<false><<<grid, 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad);
   CG_LAUNCH_CHECK();

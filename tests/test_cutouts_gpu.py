@@ -141,3 +141,59 @@ def test_device_noise_statistics():
     rec2 = rec.slice(1, 3)
     out2, _ = cutouts_forward(x.cuda(), rec2)
     assert torch.equal(out2, out[1:3])  # a shard draws the same noise as the full batch
+
+
+def test_kernels_against_committed_reference_golden():
+    """The CUDA kernels against what the REFERENCE's own cutouts.py / losses.py produced (tests/golden, generated by
+    oracle/gen_golden.py from /root/reference in the build container) -- no oracle in between."""
+    import os
+
+    from clip_diffusion_b200 import losses as L
+    from clip_diffusion_b200.cutouts import make_cutouts_from_record
+    from clip_diffusion_b200.rng_record import draw_cutout_record
+
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    for item in torch.load(os.path.join(gold, "cutouts_reference.pt")):
+        H, W, cs, no, ni, p, gp, seed = item["args"]
+        torch.manual_seed(seed)
+        rec = draw_cutout_record(H, W, cs, no, ni, p, gp, noise="cpu")  # same draws the reference made from this seed
+        out = make_cutouts_from_record(item["x"].cuda(), rec)
+        assert (out.cpu() - item["out"]).abs().max().item() <= PIXEL_TOL
+    g = torch.load(os.path.join(gold, "losses_reference.pt"))
+    x = g["x"].cuda().requires_grad_()
+    tv = L.total_variational_loss(x)
+    assert torch.allclose(tv.cpu(), g["tv"], rtol=2e-5)
+    assert ((torch.autograd.grad(tv.sum(), x)[0].cpu() - g["gtv"]).norm() / g["gtv"].norm()).item() < 1e-5
+    rg = L.rgb_range_loss(x)
+    assert torch.allclose(rg.cpu(), g["range"], rtol=2e-5)
+    assert ((torch.autograd.grad(rg.sum(), x)[0].cpu() - g["grange"]).norm() / g["grange"].norm()).item() < 1e-5
+    e = g["emb"].cuda().requires_grad_()
+    sp = L.square_spherical_distance_loss(e, g["txt"].cuda())
+    assert torch.allclose(sp.cpu(), g["sph"], rtol=1e-5, atol=1e-6)
+    assert ((torch.autograd.grad(sp.sum(), e)[0].cpu() - g["gsph"]).norm() / g["gsph"].norm()).item() < 1e-5
+
+
+def test_random_configurations_against_oracle():
+    """Seeded sweep over (H, W multiples of 32, cut size, overview/inner counts, power, gray portion): covers the <= quirk of
+    the gray portion, the non-square pad branch and the <=4 / >4 overview branches with arbitrary combinations."""
+    import random
+
+    from clip_diffusion_b200.cutouts import make_cutouts_from_record
+    from clip_diffusion_b200.rng_record import draw_cutout_record
+
+    rnd = random.Random(0)
+    for trial in range(12):
+        cs = rnd.choice([32, 64, 96])
+        H = rnd.choice([cs, cs + 32, 128, 192])
+        W = rnd.choice([cs, cs + 64, 160, 256])
+        H, W = max(H, cs), max(W, cs)
+        no, ni = rnd.randint(0, 7), rnd.randint(0, 6)
+        if no + ni == 0:
+            ni = 1
+        g = torch.Generator().manual_seed(trial)
+        x = torch.tanh(torch.randn(1, 3, H, W, generator=g)) * 1.1
+        rec = draw_cutout_record(H, W, cs, no, ni, rnd.choice([0.5, 1, 5]), rnd.choice([0.0, 0.3, 1.0]), generator=g, noise="cpu")
+        ref = OC.make_cutouts(x, rec)
+        out = make_cutouts_from_record(x.cuda(), rec)
+        err = (out.cpu() - ref).abs().max().item()
+        assert err <= PIXEL_TOL, (trial, H, W, cs, no, ni, err)
