@@ -184,9 +184,8 @@ def test_random_configurations_against_oracle():
     rnd = random.Random(0)
     for trial in range(12):
         cs = rnd.choice([32, 64, 96])
-        H = rnd.choice([cs, cs + 32, 128, 192])
-        W = rnd.choice([cs, cs + 64, 160, 256])
-        H, W = max(H, cs), max(W, cs)
+        H = rnd.choice([cs, cs + 32, 2 * cs, 3 * cs])
+        W = rnd.choice([cs, cs + 64, 2 * cs + 32, 4 * cs])  # overview crops downscale by <= 4x (kernel limit: 5x, TAPS_MAX)
         no, ni = rnd.randint(0, 7), rnd.randint(0, 6)
         if no + ni == 0:
             ni = 1
@@ -197,3 +196,13 @@ def test_random_configurations_against_oracle():
         out = make_cutouts_from_record(x.cuda(), rec)
         err = (out.cpu() - ref).abs().max().item()
         assert err <= PIXEL_TOL, (trial, H, W, cs, no, ni, err)
+
+
+def test_excessive_downscale_is_refused_loudly():
+    from clip_diffusion_b200._lib import ClipGuideError
+    from clip_diffusion_b200.cutouts import cutouts_forward
+    from clip_diffusion_b200.rng_record import draw_cutout_record
+
+    rec = draw_cutout_record(256, 256, 32, 1, 0, 5, 0.3, generator=torch.Generator().manual_seed(0), noise="cpu")
+    with pytest.raises(ClipGuideError, match="downscale ratio"):
+        cutouts_forward(torch.zeros(1, 3, 256, 256, device="cuda"), rec)
