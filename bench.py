@@ -193,7 +193,7 @@ def main():
     from clip_diffusion_b200.diffusion import SpacedDiffusion
     from clip_diffusion_b200.models import load_clip_models
     from clip_diffusion_b200.sample import GuidanceStep, make_denoised_function
-    from clip_diffusion_b200.unet import create_unet
+    from clip_diffusion_b200.unet import create_unet, graph_unet
     from clip_diffusion_b200.utils.functional import set_seed
 
     torch.cuda.set_device(local_rank)
@@ -211,13 +211,8 @@ def main():
     if unet is not None and not args.no_graphs and not args.two_forwards:
         # The replicated UNet is ~7k tiny stock-PyTorch launches per step and the step was launch-bound on the host
         # (profiles/r01_*): capture its forward and backward once into CUDA graphs (static shapes, batch 1).
-        sx = torch.randn(1, 3, size, size, device=dev, requires_grad=True)
-        st = torch.full((1,), 500.0, device=dev)
-        graphed = torch.cuda.make_graphed_callables(unet, (sx, st))
-        unet_module = unet
-        unet = lambda x, t, y=None: graphed(x, t)  # noqa: E731  (same call signature as the module)
+        unet = graph_unet(unet, size, size, dev)
         unet_graphed = True
-        del sx, st
     clip_models = load_clip_models(names, dev)
     g = torch.Generator().manual_seed(0)
     text = {n: {"embeddings": torch.randn(1, m.visual.output_dim, generator=g).to(dev), "weights": torch.tensor(1.0, device=dev)} for n, m in clip_models.items()}

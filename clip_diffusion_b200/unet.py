@@ -229,3 +229,21 @@ def create_unet(image_size=512, seed=2, device="cuda", use_fp16=True, config=Non
         torch.manual_seed(seed)
         model = UNetModel(image_size, use_fp16=use_fp16, config=config)
     return model.to(device).eval().requires_grad_(False)
+
+
+def graph_unet(model, height, width=None, device="cuda"):
+    """Capture the replicated UNet's forward AND backward into CUDA graphs (``torch.cuda.make_graphed_callables``) for a fixed
+    [1,3,H,W] input.  The UNet is ~7k small stock-PyTorch launches per guidance step and the host could not keep the GPU fed
+    (profiles/r01_*): with graphs the step is bounded by device time instead of launch overhead.  Returns a callable with the
+    module's signature ``(x, timesteps, y=None)``; ``x`` must require grad (use ``GuidanceStep.ddim_step``, which always
+    evaluates the UNet once, with grad)."""
+    width = width or height
+    sx = torch.randn(1, 3, height, width, device=device, requires_grad=True)
+    st = torch.full((1,), 500.0, device=device)
+    graphed = torch.cuda.make_graphed_callables(model, (sx, st))
+
+    def call(x, timesteps, y=None):
+        return graphed(x, timesteps.to(torch.float32))
+
+    call.module = model
+    return call
