@@ -16,29 +16,29 @@ from torch.nn import functional as F
 
 
 class _SplitStatsGroupNorm(torch.autograd.Function):
-    """GroupNorm for fp16 CUDA activations out of stock torch ops, arranged for parallelism.
+    """GroupNorm for fp16 CUDA activations out of stock torch ops, arranged for parallelism and layout independence.
 
     ATen's group-norm statistics kernel launches one CTA per (sample, group) -- 32 CTAs for the batch-1 UNet, i.e. 22% of
     a B200's SMs -- and measured 38% of the whole guidance step (profiles/r01_c2_step_kernel_table_torchprofiler.txt).
-    Here every group is split into S contiguous chunks whose mean/variance come from one `var_mean` over N*G*S rows and
-    are merged exactly (parallel-variance formula, fp32); normalisation is one `addcmul` (fp32 math, one rounding).
-    The backward uses the closed form dx = a_c*dy + b_g*x + c_g with two row reductions and two element-wise passes."""
+    Here the statistics are split per CHANNEL (N*C rows: sum and sum of squares, fp32 accumulation) and merged per group,
+    normalisation is one `addcmul` (fp32 math, one rounding), and the backward uses the closed form
+    dx = a_c*dy + b_g*x + c_g with two per-channel reductions and two element-wise passes.  Every op is dimension based, so
+    it works unchanged on channels_last tensors (no NCHW<->NHWC round trips around the cuDNN convolutions)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, groups, eps):
         n, c = x.shape[0], x.shape[1]
-        length = x.numel() // (n * groups)
-        split = 1
-        while split < 256 and length % (split * 2) == 0 and length // (split * 2) >= 2048:
-            split *= 2
-        var_s, mean_s = torch.var_mean(x.reshape(n * groups * split, length // split), dim=1, unbiased=False)
-        mean_s, var_s = mean_s.float().view(n, groups, split), var_s.float().view(n, groups, split)
-        mean = mean_s.mean(-1)
-        var = (var_s + mean_s * mean_s).mean(-1) - mean * mean
+        cg = c // groups
+        dims = tuple(range(2, x.dim()))
+        m = float(x.numel() // (n * groups))
+        s1 = x.sum(dim=dims, dtype=torch.float32)                                   # [n, c]
+        s2 = torch.linalg.vector_norm(x, 2, dim=dims, dtype=torch.float32).square()  # [n, c] sum of squares, no temporary
+        mean = s1.view(n, groups, cg).sum(-1) / m
+        var = s2.view(n, groups, cg).sum(-1) / m - mean * mean
         rstd = torch.rsqrt(var.clamp_min(0) + eps)
-        w = weight.float().view(1, groups, c // groups)
+        w = weight.float().view(1, groups, cg)
         scale = (rstd.unsqueeze(-1) * w).view(n, c)
-        shift = bias.float().view(1, c) - mean.repeat_interleave(c // groups, dim=1) * scale
+        shift = bias.float().view(1, c) - mean.repeat_interleave(cg, dim=1) * scale
         shp = (n, c) + (1,) * (x.dim() - 2)
         y = torch.addcmul(shift.to(x.dtype).view(shp), x, scale.to(x.dtype).view(shp))
         ctx.save_for_backward(x, mean, rstd, weight)
@@ -51,15 +51,13 @@ class _SplitStatsGroupNorm(torch.autograd.Function):
         g = ctx.groups
         n, c = x.shape[0], x.shape[1]
         cg = c // g
-        hw = x.numel() // (n * c)
-        dyf = dy.reshape(n, c, hw)
-        xf = x.reshape(n, c, hw)
-        s_dy = dyf.sum(-1, dtype=torch.float32)                       # [n, c]
-        s_dyx = (dyf * xf).sum(-1, dtype=torch.float32)               # [n, c]
+        dims = tuple(range(2, x.dim()))
+        m = float(x.numel() // (n * g))
+        s_dy = dy.sum(dim=dims, dtype=torch.float32)                  # [n, c]
+        s_dyx = (dy * x).sum(dim=dims, dtype=torch.float32)           # [n, c]
         w = weight.float().view(1, g, cg)
         s_dy_g = (s_dy.view(n, g, cg) * w).sum(-1)                    # sum over the group of gamma*dy
         s_dyx_g = (s_dyx.view(n, g, cg) * w).sum(-1)
-        m = float(cg * hw)
         # x_hat = (x - mean) * rstd ;  dx = rstd * (gamma*dy - mean_g(gamma*dy) - x_hat * mean_g(gamma*dy*x_hat))
         c2 = (s_dyx_g - mean * s_dy_g) * rstd / m                     # mean_g(gamma*dy*x_hat)
         c1 = s_dy_g / m
@@ -168,6 +166,7 @@ class UNetModel(nn.Module):
         mc, mult, attn_ds = config if config is not None else UNET_CONFIGS[image_size]
         self.model_channels = mc
         self.dtype = torch.float16 if use_fp16 else torch.float32
+        self.channels_last = False  # set by create_unet(..., channels_last=True): NHWC activations/weights for cuDNN
         emb_ch = mc * 4
         self.time_embed = nn.Sequential(nn.Linear(mc, emb_ch), nn.SiLU(), nn.Linear(emb_ch, emb_ch))
         ch = in_ch = int(mult[0] * mc)
@@ -210,6 +209,8 @@ class UNetModel(nn.Module):
     def forward(self, x, timesteps, y=None):
         emb = self.time_embed(timestep_embedding(timesteps, self.model_channels))
         h = x.type(self.dtype)
+        if self.channels_last:
+            h = h.contiguous(memory_format=torch.channels_last)
         hs = []
         for blk in self.input_blocks:
             h = blk(h, emb)
@@ -221,14 +222,20 @@ class UNetModel(nn.Module):
         return self.out_conv(F.silu(self.out_norm(h)))
 
 
-def create_unet(image_size=512, seed=2, device="cuda", use_fp16=True, config=None):
+def create_unet(image_size=512, seed=2, device="cuda", use_fp16=True, config=None, channels_last=None):
     """Random-init UNet (no checkpoints offline).  guided-diffusion zero-initialises the last conv of every ResBlock,
     the attention projections and the output conv; with random weights that would make epsilon identically 0, so
     they keep PyTorch's default init."""
     with torch.random.fork_rng(devices=[]):
         torch.manual_seed(seed)
         model = UNetModel(image_size, use_fp16=use_fp16, config=config)
-    return model.to(device).eval().requires_grad_(False)
+    model = model.to(device).eval().requires_grad_(False)
+    if channels_last is None:
+        channels_last = use_fp16 and torch.device(device).type == "cuda"
+    if channels_last:  # cuDNN's tensor-core convolutions are NHWC: keep everything NHWC instead of transposing around each conv
+        model = model.to(memory_format=torch.channels_last)
+        model.channels_last = True
+    return model
 
 
 def graph_unet(model, height, width=None, device="cuda"):
