@@ -20,10 +20,11 @@ class _SplitStatsGroupNorm(torch.autograd.Function):
 
     ATen's group-norm statistics kernel launches one CTA per (sample, group) -- 32 CTAs for the batch-1 UNet, i.e. 22% of
     a B200's SMs -- and measured 38% of the whole guidance step (profiles/r01_c2_step_kernel_table_torchprofiler.txt).
-    Here the statistics are split per CHANNEL (N*C rows: sum and sum of squares, fp32 accumulation) and merged per group,
-    normalisation is one `addcmul` (fp32 math, one rounding), and the backward uses the closed form
-    dx = a_c*dy + b_g*x + c_g with two per-channel reductions and two element-wise passes.  Every op is dimension based, so
-    it works unchanged on channels_last tensors (no NCHW<->NHWC round trips around the cuDNN convolutions)."""
+    Here every group is split into S contiguous chunks whose mean/variance come from one `var_mean` over N*G*S rows and
+    are merged exactly (parallel-variance formula, fp32); normalisation is one `addcmul` (fp32 math, one rounding), and the
+    backward uses the closed form dx = a_c*dy + b_g*x + c_g with two per-channel reductions and two element-wise passes.
+    A dimension-based fallback handles non-contiguous layouts (channels_last was measured: ATen's NHWC reductions cost more
+    than the cuDNN NCHW<->NHWC transposes they save -- 67 vs 63 ms/step -- so NCHW stays the default)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, groups, eps):
@@ -31,10 +32,21 @@ class _SplitStatsGroupNorm(torch.autograd.Function):
         cg = c // groups
         dims = tuple(range(2, x.dim()))
         m = float(x.numel() // (n * groups))
-        s1 = x.sum(dim=dims, dtype=torch.float32)                                   # [n, c]
-        s2 = torch.linalg.vector_norm(x, 2, dim=dims, dtype=torch.float32).square()  # [n, c] sum of squares, no temporary
-        mean = s1.view(n, groups, cg).sum(-1) / m
-        var = s2.view(n, groups, cg).sum(-1) / m - mean * mean
+        if x.is_contiguous():
+            # NCHW: every group is one contiguous run -> split it into S chunks, ONE Welford pass over N*G*S rows, exact merge
+            length, split = int(m), 1
+            while split < 256 and length % (split * 2) == 0 and length // (split * 2) >= 2048:
+                split *= 2
+            var_s, mean_s = torch.var_mean(x.reshape(n * groups * split, length // split), dim=1, unbiased=False)
+            mean_s, var_s = mean_s.float().view(n, groups, split), var_s.float().view(n, groups, split)
+            mean = mean_s.mean(-1)
+            var = (var_s + mean_s * mean_s).mean(-1) - mean * mean
+        else:
+            # any other layout (e.g. channels_last): per-channel sum / sum of squares, merged per group
+            s1 = x.sum(dim=dims, dtype=torch.float32)
+            s2 = torch.linalg.vector_norm(x, 2, dim=dims, dtype=torch.float32).square()
+            mean = s1.view(n, groups, cg).sum(-1) / m
+            var = s2.view(n, groups, cg).sum(-1) / m - mean * mean
         rstd = torch.rsqrt(var.clamp_min(0) + eps)
         w = weight.float().view(1, groups, cg)
         scale = (rstd.unsqueeze(-1) * w).view(n, c)
@@ -230,8 +242,6 @@ def create_unet(image_size=512, seed=2, device="cuda", use_fp16=True, config=Non
         torch.manual_seed(seed)
         model = UNetModel(image_size, use_fp16=use_fp16, config=config)
     model = model.to(device).eval().requires_grad_(False)
-    if channels_last is None:
-        channels_last = use_fp16 and torch.device(device).type == "cuda"
     if channels_last:  # cuDNN's tensor-core convolutions are NHWC: keep everything NHWC instead of transposing around each conv
         model = model.to(memory_format=torch.channels_last)
         model.channels_last = True
