@@ -184,3 +184,55 @@ def test_fast_groupnorm_matches_groupnorm32():
         (gr,) = torch.autograd.grad((yr * dy.float()).sum(), xr)
         assert (y.float() - yr).abs().max().item() < 2e-2
         assert ((g.float() - gr).norm() / gr.norm()).item() < 5e-3
+
+
+def test_config_c1_full_size_against_oracle():
+    """BASELINE.json configs[0] at its real size: one cond_fn guidance step, 256x256 image, 256-config guided-diffusion UNet
+    (552.8 M parameters), CLIP ViT-B/32, 12 overview + 4 inner cutouts, random-init weights -- CUDA path vs the fp32 CPU oracle."""
+    import copy
+
+    from clip_diffusion_b200 import models
+    from clip_diffusion_b200.diffusion import SpacedDiffusion
+    from clip_diffusion_b200.rng_record import draw_cutout_record
+    from clip_diffusion_b200.sample import GuidanceStep
+    from clip_diffusion_b200.unet import create_unet
+    from oracle.clip_vit import OracleCLIP
+    from oracle.cond_fn import make_conditon_function
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    class Cfg(_Cfg):
+        num_cutout_batches = 1
+        num_overview_cuts_schedule = (12,) * 1000
+        num_inner_cuts_schedule = (4,) * 1000
+
+    name = "ViT-B/32"
+    sd = models.random_clip_state_dict(name, seed=1)
+    mine = {name: models.CLIPModelB200(name, sd, "cuda")}
+    ref = {name: OracleCLIP(name, state_dict=sd)}
+    g = torch.Generator().manual_seed(0)
+    text = {name: {"embeddings": torch.randn(1, 512, generator=g), "weights": torch.tensor(1.0)}}
+    text_gpu = {name: {k: v.cuda() for k, v in text[name].items()}}
+    unet_cpu = create_unet(256, seed=2, device="cpu", use_fp16=False)
+    unet_gpu = copy.deepcopy(unet_cpu).cuda()
+    diffusion = SpacedDiffusion(steps=250)
+    x = torch.randn(1, 3, 256, 256, generator=g)
+    recs = {}
+
+    def record_source(nm, b, H, W, cs, n_over, n_inner, power, gray):
+        if (nm, b) not in recs:
+            recs[(nm, b)] = draw_cutout_record(H, W, cs, n_over, n_inner, power, gray, generator=torch.Generator().manual_seed(3), noise="cpu")
+        return recs[(nm, b)]
+
+    ct = 200
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    oracle_fn = make_conditon_function(diffusion, unet_cpu, ref, text, lambda: ct, Cfg, record_source)
+    expected = oracle_fn(x, diffusion.model_timesteps(torch.tensor([ct])))
+    step = GuidanceStep(diffusion, unet_gpu, mine, text_gpu, config=Cfg, record_source=record_source)
+    step.current_timestep = ct
+    got = step.cond_fn(x.cuda(), diffusion.model_timesteps(torch.tensor([ct], device="cuda")))
+    rel_gt = ((step.last_grad_tensor.cpu().view_as(oracle_fn.last_grad_tensor) - oracle_fn.last_grad_tensor).norm() / oracle_fn.last_grad_tensor.norm()).item()
+    rel = ((got.cpu() - expected).norm() / expected.norm()).item()
+    assert rel_gt <= GRAD_REL_MAX, rel_gt
+    assert rel <= GRAD_REL_MAX, rel

@@ -206,3 +206,19 @@ def test_excessive_downscale_is_refused_loudly():
     rec = draw_cutout_record(256, 256, 32, 1, 0, 5, 0.3, generator=torch.Generator().manual_seed(0), noise="cpu")
     with pytest.raises(ClipGuideError, match="downscale ratio"):
         cutouts_forward(torch.zeros(1, 3, 256, 256, device="cuda"), rec)
+
+
+def test_cutouts_forward_input_in_unit_range():
+    """Cutouts.forward takes the image already in [0,1] (cutouts.py:47); make_cutouts takes [-1,1] and denormalises."""
+    from clip_diffusion_b200.cutouts import make_cutouts_from_record
+
+    x, rec = _record(CASES[0])
+    x01 = x.add(1).div(2)
+    ref = OC.augment(OC.base_cutouts(x01, rec), rec)
+    out = make_cutouts_from_record(x01.cuda(), rec, input01=True)
+    assert (out.cpu() - ref).abs().max().item() <= PIXEL_TOL
+    xg = x01.cuda().requires_grad_()
+    (g01,) = torch.autograd.grad(make_cutouts_from_record(xg, rec, input01=True).sum(), xg)
+    xm = x.cuda().requires_grad_()
+    (gm1,) = torch.autograd.grad(make_cutouts_from_record(xm, rec, input01=False).sum(), xm)
+    assert ((g01 * 0.5 - gm1).norm() / gm1.norm()).item() < 1e-5  # d((x+1)/2)/dx = 1/2
