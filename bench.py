@@ -198,6 +198,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.benchmark = os.environ.get("CG_CUDNN_BENCHMARK", "1") == "1"  # let cuDNN pick conv algorithms for the static UNet shapes
     _lib.check(_lib.load().cg_check_device(), "cg_check_device")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
