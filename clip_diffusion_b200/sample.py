@@ -88,6 +88,14 @@ def make_denoised_function(dynamic_thresholding_percentile=0.995):
     next widening step); part of the benchmarked step because the reference passes it as ``denoised_fn`` (sample.py:254,268)."""
 
     def denoised_function(x_start):
+        if x_start.is_cuda and x_start.dtype == torch.float32:
+            # radix-select kernel (csrc/select.cu): same threshold as torch.quantile, no sort
+            xs = x_start.contiguous()
+            b, n = xs.shape[0], xs.numel() // xs.shape[0]
+            out = torch.empty_like(xs)
+            ws = torch.empty(_lib.load().cg_dynamic_threshold_workspace_bytes(b), dtype=torch.uint8, device=xs.device)
+            _lib.call("cg_dynamic_threshold", _lib.ptr(xs), b, n, float(dynamic_thresholding_percentile), 1.0, _lib.ptr(out), None, _lib.ptr(ws))
+            return out
         threshold = torch.quantile(x_start.reshape(x_start.shape[0], -1).abs().float(), dynamic_thresholding_percentile, dim=-1)
         threshold = threshold.clamp(min=1.0).view(-1, *((1,) * (x_start.ndim - 1))).to(x_start.dtype)
         return x_start.clamp(min=-threshold, max=threshold) / threshold

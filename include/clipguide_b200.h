@@ -175,6 +175,14 @@ int cg_grad_finalize(const float* g, int64_t n, float sign, float thr, const flo
 /* any(isnan(g)) -> flag[0] (1.0f/0.0f), device side; flag must have room for 2 floats. */
 int cg_any_nan(const float* g, int64_t n, float* flag, void* stream);
 
+/* ------------------------------------------------------------------ sampler side (next row N2) ---- */
+/* denoised_function, clip_diffusion/sample.py:116-132 (Imagen dynamic thresholding of the x0 prediction):
+ *   thr[b] = max(quantile(|x[b,:]|, q) , min_thr)  with torch.quantile's "linear" interpolation;  out = clamp(x,-thr,thr)/thr.
+ * x, out [B, n] fp32 (may alias); thr_out [B] optional.  Exact radix select instead of torch.quantile's sort. */
+size_t cg_dynamic_threshold_workspace_bytes(int B);
+int cg_dynamic_threshold(const float* x, int B, int64_t n, float q, float min_thr, float* out, float* thr_out, void* workspace,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

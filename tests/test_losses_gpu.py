@@ -79,3 +79,34 @@ def test_cpu_tensor_is_refused():
 
     with pytest.raises(ClipGuideError):
         L.total_variational_loss(torch.zeros(1, 3, 8, 8))
+
+
+@pytest.mark.parametrize("shape,q", [((1, 3, 512, 512), 0.995), ((2, 3, 64, 96), 0.995), ((1, 3, 37, 53), 0.5), ((3, 1000), 0.999), ((1, 3, 256, 256), 1.0),
+                                     ((1, 7), 0.3)])
+def test_dynamic_threshold_matches_torch_quantile(shape, q):
+    """sample.py:116-132 (Imagen dynamic thresholding): radix-select kernel vs torch.quantile + clamp/div."""
+    from clip_diffusion_b200 import _lib
+
+    g = torch.Generator().manual_seed(len(shape) * 131 + shape[-1])
+    x = (torch.randn(shape, generator=g) * 1.5).cuda()
+    if shape == (1, 3, 37, 53):
+        x[0, 0, :5] = 0.75  # ties around the selected rank
+    b, n = shape[0], x.numel() // shape[0]
+    thr_ref = torch.quantile(x.reshape(b, -1).abs(), q, dim=-1).clamp(min=1.0)
+    ref = x.clamp(min=-thr_ref.view(-1, *([1] * (x.dim() - 1))), max=thr_ref.view(-1, *([1] * (x.dim() - 1)))) / thr_ref.view(-1, *([1] * (x.dim() - 1)))
+    out = torch.empty_like(x)
+    thr = torch.empty(b, device="cuda")
+    ws = torch.empty(_lib.load().cg_dynamic_threshold_workspace_bytes(b), dtype=torch.uint8, device="cuda")
+    _lib.call("cg_dynamic_threshold", _lib.ptr(x), b, n, q, 1.0, _lib.ptr(out), _lib.ptr(thr), _lib.ptr(ws))
+    assert torch.allclose(thr, thr_ref, rtol=2e-7, atol=0), (thr, thr_ref)
+    assert (out - ref).abs().max().item() <= 1e-6
+
+
+def test_make_denoised_function_uses_the_kernel_and_matches_the_torch_path():
+    from clip_diffusion_b200.sample import make_denoised_function
+
+    f = make_denoised_function(0.995)
+    x = torch.randn(1, 3, 128, 128, device="cuda") * 2
+    a = f(x)
+    b = f(x.double()).float()  # non-fp32 input takes the torch.quantile path
+    assert (a - b).abs().max().item() <= 2e-6
