@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libclipguide_b200.so")
 
 CG_FMT_F32_NCHW = 0
 CG_FMT_BF16_PATCH = 1
+CG_FMT_F32_PATCH = 2
 
 EPI_BIAS_BF16 = 0
 EPI_BIAS_RESID_F32 = 1
@@ -76,7 +77,7 @@ _SIGNATURES = {
     "cg_vit_proj_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "cg_vit_tokens_to_bf16": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "cg_patchify_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
-    "cg_patchify_bwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "cg_patchify_bwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "cg_grad_finalize": (_I, [_P, _L, _F, _F, _P, _P, _P, _P]),
     "cg_any_nan": (_I, [_P, _L, _P, _P]),
     "cg_dynamic_threshold_workspace_bytes": (C.c_size_t, [_I]),

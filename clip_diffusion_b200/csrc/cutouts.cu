@@ -597,6 +597,11 @@ __device__ __forceinline__ void load_dout(const void* dout, int fmt, int n, int 
   if (fmt == CG_FMT_F32_NCHW) {
     const float* p = reinterpret_cast<const float*>(dout) + (size_t)n * 3 * pp + pix;
     d[0] = p[0]; d[1] = p[pp]; d[2] = p[2 * pp];
+  } else if (fmt == CG_FMT_F32_PATCH) {
+    const int oy = pix / cs, ox = pix - oy * cs;
+    const float* p = reinterpret_cast<const float*>(dout);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[c] = p[patch_offset(n, oy, ox, c, cs, patch, kpad)];
   } else {
     const int oy = pix / cs, ox = pix - oy * cs;
     const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(dout);

@@ -136,8 +136,8 @@ __constant__ float c_clip_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
 // thread per (n, patch j, k) of the output row-major [N*g2, kpad]; reads are patch-row contiguous
 template <bool BWD>
-__global__ void __launch_bounds__(256) patchify_kernel(float* __restrict__ img, __nv_bfloat16* __restrict__ pm, int cs, int patch, int kpad,
-                                                       int normalize, long long total) {
+__global__ void __launch_bounds__(256) patchify_kernel(float* __restrict__ img, __nv_bfloat16* __restrict__ pm, const float* __restrict__ pm32, int cs,
+                                                       int patch, int kpad, int normalize, long long total) {
   const int g = cs / patch, pp = patch * patch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % kpad);
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(float* __restrict__ img, 
       if (normalize) v = (v - c_clip_mean[c]) / c_clip_std[c];
       pm[i] = __float2bfloat16(v);
     } else {
-      float v = __bfloat162float(pm[i]);
+      float v = pm32 ? pm32[i] : __bfloat162float(pm[i]);
       if (normalize) v = v / c_clip_std[c];
       img[io] = v;
     }
@@ -235,20 +235,21 @@ extern "C" int cg_patchify_fwd(const float* img, int N, int cs, int patch, int k
   const long long total = (long long)N * g * g * kpad;
   long long blocks = (total + 255) / 256;
   if (blocks > CG_NUM_SMS * 16) blocks = CG_NUM_SMS * 16;
-  patchify_kernel<false><<<(unsigned)blocks, 256, 0, cg_stream(stream)>>>(const_cast<float*>(img), reinterpret_cast<__nv_bfloat16*>(out_bf16), cs, patch, kpad,
-                                                                         normalize, total);
+  patchify_kernel<false><<<(unsigned)blocks, 256, 0, cg_stream(stream)>>>(const_cast<float*>(img), reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, cs,
+                                                                         patch, kpad, normalize, total);
   CG_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int cg_patchify_bwd(const void* dpatch_bf16, int N, int cs, int patch, int kpad, int normalize, float* dimg, void* stream) {
-  CG_REQUIRE(dpatch_bf16 && dimg && N > 0 && cs > 0 && patch > 0 && cs % patch == 0 && kpad >= 3 * patch * patch, "cg_patchify_bwd: bad arguments");
+extern "C" int cg_patchify_bwd(const void* dpatch, int dpatch_is_f32, int N, int cs, int patch, int kpad, int normalize, float* dimg, void* stream) {
+  CG_REQUIRE(dpatch && dimg && N > 0 && cs > 0 && patch > 0 && cs % patch == 0 && kpad >= 3 * patch * patch, "cg_patchify_bwd: bad arguments");
   const int g = cs / patch;
   const long long total = (long long)N * g * g * kpad;
   long long blocks = (total + 255) / 256;
   if (blocks > CG_NUM_SMS * 16) blocks = CG_NUM_SMS * 16;
-  patchify_kernel<true><<<(unsigned)blocks, 256, 0, cg_stream(stream)>>>(dimg, const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(dpatch_bf16)), cs,
-                                                                        patch, kpad, normalize, total);
+  patchify_kernel<true><<<(unsigned)blocks, 256, 0, cg_stream(stream)>>>(
+      dimg, dpatch_is_f32 ? nullptr : const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(dpatch)),
+      dpatch_is_f32 ? reinterpret_cast<const float*>(dpatch) : nullptr, cs, patch, kpad, normalize, total);
   CG_LAUNCH_CHECK();
   return 0;
 }

@@ -96,6 +96,8 @@ def cutouts_backward(dout, ctx, coef=1.0, dx_in=None):
     if dx_in is None:
         dx_in = torch.empty(3, H, W, device=dout.device, dtype=torch.float32)
     dout = dout.contiguous()
+    if fmt == _lib.CG_FMT_BF16_PATCH and dout.dtype == torch.float32:
+        fmt = _lib.CG_FMT_F32_PATCH  # the conv1 dgrad GEMM hands over fp32 patch-major gradients
     _lib.call("cg_cutouts_bwd", _lib.ptr(dout), H, W, n, cs, fmt, patch, kpad, float(coef), int(accumulate), input01, _lib.ptr(dx_in), _lib.ptr(ws))
     return dx_in
 

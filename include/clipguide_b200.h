@@ -96,6 +96,7 @@ typedef struct {
 /* output formats of cg_cutouts_fwd / input format of cg_cutouts_bwd */
 #define CG_FMT_F32_NCHW 0   /* [N,3,cs,cs] fp32 -- what make_cutouts returns */
 #define CG_FMT_BF16_PATCH 1 /* [N, g*g, kpad] bf16, k = c*p*p + py*p + px: the im2col rows of CLIP's conv1 */
+#define CG_FMT_F32_PATCH 2  /* same layout in fp32: the conv1 dgrad GEMM's output, accepted by cg_cutouts_bwd as `dout` */
 
 size_t cg_cutouts_workspace_bytes(int N, int cs, int max_size);
 
@@ -163,7 +164,7 @@ int cg_vit_tokens_to_bf16(const float* x, int Nimg, int T, int D, int drop_cls, 
  * then conv1's im2col rows:  img [N,3,cs,cs] fp32 -> out [N, (cs/patch)^2, kpad] bf16 (pad zeroed); and its
  * backward dpatch -> dimg. */
 int cg_patchify_fwd(const float* img, int N, int cs, int patch, int kpad, int normalize, void* out_bf16, void* stream);
-int cg_patchify_bwd(const void* dpatch_bf16, int N, int cs, int patch, int kpad, int normalize, float* dimg, void* stream);
+int cg_patchify_bwd(const void* dpatch, int dpatch_is_f32, int N, int cs, int patch, int kpad, int normalize, float* dimg, void* stream);
 
 /* ------------------------------------------------------------------ cond_fn tail ---------- */
 /* sample.py:228-238: NaN guard + RMS-normalised clamp, on device (no host sync):

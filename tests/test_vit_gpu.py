@@ -136,5 +136,5 @@ def test_patchify_roundtrip():
     _lib.call("cg_patchify_fwd", _lib.ptr(img), n, cs, patch, kpad, 0, _lib.ptr(pm))
     assert (pm[:, :, 3 * patch * patch:] == 0).all()
     back = torch.empty_like(img)
-    _lib.call("cg_patchify_bwd", _lib.ptr(pm), n, cs, patch, kpad, 0, _lib.ptr(back))
+    _lib.call("cg_patchify_bwd", _lib.ptr(pm), 0, n, cs, patch, kpad, 0, _lib.ptr(back))
     assert (back - img).abs().max().item() < 4e-3  # bf16 rounding of values in [0,1]
