@@ -162,7 +162,7 @@ def run_reference(args, rank):
     k = max(1, min(args.steps, int((args.cpu_budget_s - t_first) / max(t_first, 1e-3))))
     t0 = time.time()
     for j in range(k):
-        i -= 1
+        i = i - 1 if i > 0 else ddim - 1
         x = step(x, i)
     dt = (time.time() - t0) / k
     val = 1.0 / dt
@@ -250,9 +250,12 @@ def main():
     W, K = max(args.warmup, 3), args.steps
     i = ddim - 1
     x = x_dev
+    def next_i(i):  # walk the DDIM schedule downwards, wrapping so that any --steps/--warmup works
+        return i - 1 if i > 0 else ddim - 1
+
     for _ in range(W):
         x = step(x, i)["sample"]
-        i -= 1
+        i = next_i(i)
     # ---- timed region 1: inputs resident in HBM -------------------------------------------------
     barrier()
     clocks = ClockSampler(local_rank) if rank == 0 else None
@@ -266,7 +269,7 @@ def main():
     e0.record()
     for _ in range(K):
         x = step(x, i)["sample"]
-        i -= 1
+        i = next_i(i)
     e1.record()
     barrier()
     if use_range:
@@ -287,9 +290,7 @@ def main():
         out_host[0].copy_(out["sample"][0], non_blocking=True)
         out_host[1].copy_(out["pred_xstart"][0].float(), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller consumes the step result (PNG every step, sample.py:290-295)
-        i -= 1
-        if i < 0:
-            i = ddim - 1
+        i = next_i(i)
     e1.record()
     barrier()
     ms_e2e = tmax(e0.elapsed_time(e1))
