@@ -33,6 +33,10 @@ WORKLOADS = {
     "c2": (512, ("ViT-B/16",), 16, 16, 1, 250, "512x512 uncond guided-diffusion UNet + ViT-B/16, 16 overview + 16 inner cutouts, DDIM-250"),
     "c3": (512, ("ViT-B/32", "ViT-B/16", "ViT-L/14"), 32, 32, 1, 250, "512x512 UNet + ViT-B/32+B/16+L/14 ensemble, 64 cutouts per model, tv+range"),
     "target": (512, ("ViT-L/14",), 32, 32, 1, 250, "512x512 UNet + ViT-L/14, 64 cutouts (north_star target)"),
+    "c4": (512, ("ViT-B/32", "ViT-B/16", "ViT-L/14"), 8, 8, 1, 250, "512x512 UNet + B/32+B/16+L/14 with aesthetic-predictor loss (aesthetic_scale 500), 16 cutouts per model; "
+           "the init-image LPIPS/MS-SSIM terms of config 4 are outside this path (SURVEY 8(f) N3)"),
+    "c5": (768, ("ViT-L/14@336px",), 64, 64, 1, 250, "768x768 UNet + ViT-L/14@336px, 128 cutouts (cutout-scaling sweep, smallest point)"),
+    "c5-512": (768, ("ViT-L/14@336px",), 256, 256, 1, 250, "768x768 UNet + ViT-L/14@336px, 512 cutouts (cutout-scaling sweep, largest point; shard over 8 GPUs)"),
     "clip-only": (512, ("ViT-L/14",), 32, 32, 1, 250, "ViT-L/14, 64 cutouts, guidance gradient only (no UNet)"),
 }
 
@@ -217,7 +221,13 @@ def main():
     clip_models = load_clip_models(names, dev)
     g = torch.Generator().manual_seed(0)
     text = {n: {"embeddings": torch.randn(1, m.visual.output_dim, generator=g).to(dev), "weights": torch.tensor(1.0, device=dev)} for n, m in clip_models.items()}
-    guidance = GuidanceStep(diffusion, unet, clip_models, text, config=cfg, rank=rank, world_size=world,
+    predictors = None
+    if args.workload == "c4":
+        from clip_diffusion_b200.models import load_aesthetic_predictors
+
+        cfg.aesthetic_scale = 500
+        predictors = load_aesthetic_predictors(names, dev)
+    guidance = GuidanceStep(diffusion, unet, clip_models, text, aesthetic_predictors=predictors, config=cfg, rank=rank, world_size=world,
                             range_scale=150.0 if args.workload == "c3" else 0.0)
     denoised_fn = make_denoised_function(0.995)  # reference defaults: dynamic thresholding 0.995, eta 0.8 (sample.py:66-71)
     cuts_per_step = (n_over + n_inner) * batches * len(names)
