@@ -7,8 +7,10 @@ A "step" is ONE full CLIP-guided DDIM sampling step on synthetic inputs: the sam
 guidance function (UNet forward with grad -> fused cutouts -> CLIP ViT fwd -> spherical loss+grad -> ViT dgrad ->
 cutout backward -> TV -> all-reduce -> UNet VJP -> RMS clamp) and the DDIM update.  Default workload = BASELINE.json
 configs[1]: 512x512 uncond guided-diffusion UNet (fp16, random init) + ViT-B/16, 16 overview + 16 inner cutouts,
-DDIM-250 schedule.  For N > 1 the cutout batch is sharded across ranks (one NCCL all-reduce of the [3,512,512] fp32
-image gradient per step, UNet replicated) => strong scaling.
+DDIM-250 schedule.  `value` is cutouts/s = steps/s x cutouts per step (steps/s is reported beside it as `steps_per_s`): SURVEY
+section 7 -- cutouts/s is the quantity that scales with GPUs, steps/s is bounded by the replicated UNet.  For N > 1 the cutout
+batch of every step is sharded across ranks (one NCCL all-reduce of the [3,512,512] fp32 image gradient per step, UNet
+replicated); --scaling weak (default) keeps the workload's cutouts PER RANK (N x cutouts per step), --scaling strong splits them.
 
 --impl reference times the CPU restatement of the reference path (oracle/, fp32, all host threads) on the same
 workload; see cpu_baseline in the JSON line.
@@ -48,6 +50,9 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                   help="N>1: weak = every rank keeps the workload's cutouts (N x cutouts per step, value in cutouts/s scales); "
+                        "strong = the workload's cutouts are split over the ranks")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graphs", action="store_true", help="do not capture the replicated UNet forward/backward into CUDA graphs")
     p.add_argument("--two-forwards", action="store_true", help="evaluate the UNet separately for the sampler and for cond_fn like the reference does")
@@ -114,7 +119,17 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def build_cpu_reference(wl, seed=0):
+def scaled_cuts(wl, world, scaling):
+    """(overview, inner) cutouts of one (model, batch): the workload's counts, times the world size under weak scaling."""
+    n_over, n_inner = WORKLOADS[wl][2], WORKLOADS[wl][3]
+    mult = world if (scaling == "weak" and world > 1) else 1
+    return n_over * mult, n_inner * mult
+
+
+METRIC = "CLIP-guided cutouts/s fwd+bwd inside full guidance steps (= steps/s x cutouts per step) @%dx%d"
+
+
+def build_cpu_reference(wl, seed=0, world=1, scaling="weak"):
     """The CPU restatement of the reference path (oracle/): same workload, fp32, torch CPU ops."""
     from clip_diffusion_b200.diffusion import SpacedDiffusion  # sampler host logic (numpy + torch ops), not a kernel
     from clip_diffusion_b200.models import random_clip_state_dict
@@ -123,7 +138,8 @@ def build_cpu_reference(wl, seed=0):
     from oracle.clip_vit import OracleCLIP
     from oracle.cond_fn import make_conditon_function
 
-    size, names, n_over, n_inner, batches, ddim, _ = WORKLOADS[wl]
+    size, names, _, _, batches, ddim, _ = WORKLOADS[wl]
+    n_over, n_inner = scaled_cuts(wl, world, scaling)
     cfg = make_cfg(n_over, n_inner, batches)
     unet = create_unet(size if size in (256, 512) else 512, seed=2, device="cpu", use_fp16=False)
     diffusion = SpacedDiffusion(steps=ddim)
@@ -158,7 +174,7 @@ def run_reference(args, rank):
     wl = args.workload
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(1234)
-    step, x, ddim, cuts = build_cpu_reference(wl)
+    step, x, ddim, cuts = build_cpu_reference(wl, world=args.gpus, scaling=args.scaling)
     t0 = time.time()
     i = ddim - 1
     x = step(x, i)  # warm-up (also sizes the timed part)
@@ -172,12 +188,12 @@ def run_reference(args, rank):
     val = 1.0 / dt
     sample = "%d full guidance step(s) after 1 warm-up step (requested %d/%d; bounded to %.0f s of CPU time)" % (k, args.steps, args.warmup, args.cpu_budget_s)
     line = {
-        "impl": "reference", "metric": "CLIP-guided DDIM steps/s @%dx%d" % (WORKLOADS[wl][0], WORKLOADS[wl][0]), "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": k,
-        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference", "metric": METRIC % (WORKLOADS[wl][0], WORKLOADS[wl][0]), "value": cuts * val, "unit": "cutouts/s", "n_gpus": args.gpus, "steps": k,
+        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[wl][6], "cutouts_per_step": cuts},
-        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "cutouts_per_s": cuts * val,
+        "cpu_baseline": {"value": cuts * val, "unit": "cutouts/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": cuts * val, "unit": "cutouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "steps_per_s": val,
     }
     print(json.dumps(line), flush=True)
 
@@ -206,7 +222,8 @@ def main():
     _lib.check(_lib.load().cg_check_device(), "cg_check_device")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    size, names, n_over, n_inner, batches, ddim, desc = WORKLOADS[args.workload]
+    size, names, _, _, batches, ddim, desc = WORKLOADS[args.workload]
+    n_over, n_inner = scaled_cuts(args.workload, world, args.scaling)
     cfg = make_cfg(n_over, n_inner, batches)
     set_seed(1234)
     clip_only = args.workload == "clip-only"
@@ -319,13 +336,13 @@ def main():
     e2e = K / (ms_e2e / 1e3)
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     line = {
-        "metric": "CLIP-guided DDIM steps/s @%dx%d" % (size, size), "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "metric": METRIC % (size, size), "value": cuts_per_step * value, "unit": "cutouts/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "cutouts_per_step": cuts_per_step, "cutouts_per_rank": -(-cuts_per_step // world), "unet_cuda_graphs": unet_graphed, "unet": "fp16 stock PyTorch, replicated; %s" % ("two forwards per step (sampler + cond_fn) like the reference" if args.two_forwards else "one grad-enabled forward shared by sampler and cond_fn (identical results)"),
-                   "clip": "bf16 operands / fp32 accumulate + fp32 residual stream, random init", "parallelism": "cutouts sharded x%d, 1 all-reduce/step" % world,
+                   "clip": "bf16 operands / fp32 accumulate + fp32 residual stream, random init", "parallelism": "%d cutouts per (model, step) sharded over %d rank(s) = %d per rank, 1 all-reduce of the image gradient per step" % (n_over + n_inner, world, -(-(n_over + n_inner) // world)),
                    "l2": "working set (1.1 GB UNet + ViT weights + activations) far exceeds the 126 MB L2; no flush"},
-        "cutouts_per_s": cuts_per_step * value,
-        "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
+        "steps_per_s": value,
+        "e2e": {"value": cuts_per_step * e2e, "unit": "cutouts/s", "steps_per_s": e2e, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM/TMA, all ViT GEMMs)", "achieved": achieved, "peak": tf_peak,
@@ -335,11 +352,11 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline and not clip_only:
         torch.set_num_threads(os.cpu_count() or 1)
-        cstep, cx, cddim, _ = build_cpu_reference(args.workload)
+        cstep, cx, cddim, ccuts = build_cpu_reference(args.workload)
         t0 = time.time()
         cstep(cx, cddim - 1)
         dt = time.time() - t0
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+        line["cpu_baseline"] = {"value": ccuts / dt, "unit": "cutouts/s", "steps_per_s": 1.0 / dt, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "1 full guidance step of the same workload, fp32, no warm-up (%.1f s)" % dt}
     print(json.dumps(line), flush=True)
     if world > 1:
