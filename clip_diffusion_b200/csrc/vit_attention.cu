@@ -400,8 +400,15 @@ static int pick_warps(int T) {
   return best;
 }
 
+int cg_attention_fwd_tc(const void* qkv, int Nimg, int T, int heads, void* ctx, float* lse, cudaStream_t s);  // vit_attention_tc.cu
+
 extern "C" int cg_attention_fwd(const void* qkv, int Nimg, int T, int heads, void* ctx, float* lse, void* stream) {
   CG_REQUIRE(qkv && ctx && lse && Nimg > 0 && T > 0 && heads > 0, "cg_attention_fwd: bad arguments");
+  {
+    // tcgen05/TMEM path for T <= 272 (all 224-pixel towers); returns 1 when it does not apply (T too long or CG_ATTN_TC=0)
+    const int rc_tc = cg_attention_fwd_tc(qkv, Nimg, T, heads, ctx, lse, cg_stream(stream));
+    if (rc_tc != 1) return rc_tc;
+  }
   const int Tp = (T + 63) & ~63;
   CG_REQUIRE(Tp <= 640, "cg_attention_fwd: T=%d exceeds the shared-memory resident limit (640)", T);
   const int W = pick_warps(T);
