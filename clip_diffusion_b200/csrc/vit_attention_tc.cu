@@ -10,7 +10,8 @@
 //   epilogue   O / l -> bf16 ctx, log-sum-exp -> lse (the backward recomputes P from it)
 //
 // The scores never leave the SM; the two GEMMs of a head run on the tensor cores at M=128 instead of the 16-row
-// mma.sync tiles of vit_attention.cu (which remains the path for T > 272 and for the backward).
+// mma.sync tiles of vit_attention.cu.  EXPERIMENTAL (CG_ATTN_TC=1): validated against the oracle, not yet faster -- see
+// cg_attention_fwd_tc below; vit_attention.cu remains the default path (and the only one for T > 272 and the backward).
 #include <stdlib.h>
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -216,7 +217,10 @@ int cg_attention_fwd_tc(const void* qkv, int Nimg, int T, int heads, void* ctx, 
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("CG_ATTN_TC");
-    enabled = e ? (atoi(e) != 0) : 1;
+    // Off by default: parity-green on B200, but one CTA/SM with serialised TMA -> MMA -> softmax -> MMA phases measured
+    // 151 us/layer (ViT-L/14 x 64) against 106 us for the 2-CTA/SM mma.sync kernel.  Needs a persistent CTA with K/V
+    // prefetch and CUDA-core handling of the 1-row remainder tile (T = 257 = 2*128 + 1) before it pays off (round 2).
+    enabled = e ? (atoi(e) != 0) : 0;
   }
   if (!enabled) return 1;
   const int D = heads * 64;
