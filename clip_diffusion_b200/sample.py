@@ -21,16 +21,18 @@ import torch
 from clip_diffusion_b200 import _lib
 from clip_diffusion_b200.config import Config
 from clip_diffusion_b200.cutouts import _device_noise_seed, cutouts_backward, cutouts_forward, make_cutouts
-from clip_diffusion_b200.losses import aesthetic_loss, square_spherical_distance_loss, total_variational_loss
+from clip_diffusion_b200.losses import (LPIPS_loss, aesthetic_loss, square_spherical_distance_loss, structural_dissimilarity_loss,
+                                        total_variational_loss)
 from clip_diffusion_b200.rng_record import draw_cutout_record
 from clip_diffusion_b200.utils.functional import embed_image
 
 
 def make_conditon_function(diffusion, model, clip_models, text_embeddings_and_weights, get_current_timestep, aesthetic_predictors=None,
-                           config=Config):
+                           config=Config, init_image_tensor=None, LPIPS_model=None):
     """sample.py:134-238 (the typo in the name is the reference's).  ``get_current_timestep()`` returns the respaced
-    index the outer loop maintains (sample.py:285-288).  The init-image branch (LPIPS / MS-SSIM, sample.py:220-225)
-    is outside this path."""
+    index the outer loop maintains (sample.py:285-288).  With ``init_image_tensor`` the init-image branch
+    (sample.py:220-225) is evaluated with the caller's ``LPIPS_model`` (the un-vendored VGG LPIPS; skipped when None) and
+    the torch MS-SSIM of losses.py -- stock PyTorch, not part of the kernel path."""
     aesthetic_predictors = aesthetic_predictors or {}
 
     @torch.enable_grad()
@@ -71,6 +73,11 @@ def make_conditon_function(diffusion, model, clip_models, text_embeddings_and_we
                 grad_tensor += torch.autograd.grad(objective, denoised_prediction)[0] / config.num_cutout_batches
         denoise_loss = total_variational_loss(denoised_prediction)
         loss_sum = denoise_loss.sum() * config.denoise_scale
+        if init_image_tensor is not None:  # sample.py:220-225
+            dissimilarity_loss = structural_dissimilarity_loss(denoised_prediction, init_image_tensor)
+            loss_sum = loss_sum + dissimilarity_loss.sum() * getattr(config, "MS_SSIM_scale", 0)
+            if LPIPS_model is not None:
+                loss_sum = loss_sum + LPIPS_loss(LPIPS_model, denoised_prediction, init_image_tensor).sum() * getattr(config, "LPIPS_scale", 0)
         grad_tensor += torch.autograd.grad(loss_sum, denoised_prediction)[0]
         if not torch.isnan(grad_tensor).any():
             grad = -torch.autograd.grad(denoised_prediction, x, grad_tensor)[0]
@@ -115,7 +122,7 @@ class GuidanceStep:
     like the closure variable of sample.py:113,285-288."""
 
     def __init__(self, diffusion, model, clip_models, text_embeddings_and_weights, aesthetic_predictors=None, config=Config,
-                 rank=0, world_size=1, process_group=None, range_scale=0.0, record_source=None):
+                 rank=0, world_size=1, process_group=None, range_scale=0.0, record_source=None, init_image_tensor=None, LPIPS_model=None):
         self.diffusion, self.model, self.clip_models = diffusion, model, clip_models
         self.text = text_embeddings_and_weights
         self.aesthetic_predictors = aesthetic_predictors or {}
@@ -125,6 +132,8 @@ class GuidanceStep:
         # optional callable (name, batch, H, W, cs, n_over, n_inner, power, gray) -> CutoutRecord replacing the global-RNG
         # draw (parity tests feed the oracle and the kernels one explicit record)
         self.record_source = record_source
+        # init-image branch (sample.py:220-225): stock-PyTorch LPIPS (caller's network) + MS-SSIM terms, replicated on every rank
+        self.init_image_tensor, self.LPIPS_model = init_image_tensor, LPIPS_model
         self.current_timestep = None
         self.last_records = []  # RNG records of the latest call, per (model, cutout batch)
         self.cutouts_processed = 0
@@ -227,6 +236,14 @@ class GuidanceStep:
         _lib.call("cg_tv_loss_fwd_bwd", _lib.ptr(x_in), 1, 3, H, W, float(cfg.denoise_scale), 1, None, _lib.ptr(grad_tensor))
         if self.range_scale:
             _lib.call("cg_range_loss_fwd_bwd", _lib.ptr(x_in), 1, 3, H, W, float(self.range_scale), 1, None, _lib.ptr(grad_tensor))
+        if self.init_image_tensor is not None:
+            with torch.enable_grad():
+                xi = x_in.view(1, *x_in.shape[-3:]).detach().requires_grad_()
+                extra = structural_dissimilarity_loss(xi, self.init_image_tensor).sum() * getattr(cfg, "MS_SSIM_scale", 0)
+                if self.LPIPS_model is not None:
+                    extra = extra + LPIPS_loss(self.LPIPS_model, xi, self.init_image_tensor).sum() * getattr(cfg, "LPIPS_scale", 0)
+                (gi,) = torch.autograd.grad(extra, xi)
+            grad_tensor += gi.view_as(grad_tensor)
         if self._scratch is None:
             self._scratch = torch.zeros(4, device=x.device, dtype=torch.float32)
         flag, scratch = self._scratch[:2], self._scratch[2:]

@@ -112,3 +112,22 @@ def test_diffusion_schedule_and_unet():
         n512 = sum(p.numel() for p in UNetModel(512, use_fp16=False).parameters())
         n256 = sum(p.numel() for p in UNetModel(256, use_fp16=False).parameters())
     assert abs(n512 / 1e6 - 558.0) < 0.1 and abs(n256 / 1e6 - 552.8) < 0.1  # SURVEY.md App. A.3 parameter counts
+
+
+def test_ms_ssim_restatement_properties():
+    """losses.ms_ssim (restated pytorch_msssim.MS_SSIM, parity unpinned): identity, symmetry, monotone in noise, differentiable."""
+    from clip_diffusion_b200.losses import ms_ssim, structural_dissimilarity_loss
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 176, 192, generator=g)
+    assert abs(ms_ssim(x, x).item() - 1.0) < 1e-6
+    vals = [ms_ssim(x, (x + s * torch.randn(x.shape, generator=g)).clamp(0, 1)).item() for s in (0.02, 0.1, 0.3)]
+    assert 1.0 > vals[0] > vals[1] > vals[2] > 0.0
+    y = torch.rand(2, 3, 176, 192, generator=g)
+    assert abs(ms_ssim(x, y).item() - ms_ssim(y, x).item()) < 1e-6
+    xx = (x * 2 - 1).requires_grad_()
+    loss = structural_dissimilarity_loss(xx, y * 2 - 1)
+    (gr,) = torch.autograd.grad(loss, xx)
+    assert 0.0 < loss.item() < 1.0 and torch.isfinite(gr).all() and gr.abs().max().item() > 0
+    with pytest.raises(ValueError):
+        ms_ssim(x[..., :100, :100], y[..., :100, :100])
