@@ -56,6 +56,8 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graphs", action="store_true", help="do not capture the replicated UNet forward/backward into CUDA graphs")
     p.add_argument("--two-forwards", action="store_true", help="evaluate the UNet separately for the sampler and for cond_fn like the reference does")
+    p.add_argument("--unet-layout", default="nhwc", choices=["nhwc", "nchw"],
+                   help="nhwc (default): channels_last trunk + fused GroupNorm/scale-shift/SiLU kernels (csrc/unet_norm.cu); nchw: stock torch ops")
     p.add_argument("--cpu-budget-s", type=float, default=240.0)
     return p.parse_args()
 
@@ -227,7 +229,7 @@ def main():
     cfg = make_cfg(n_over, n_inner, batches)
     set_seed(1234)
     clip_only = args.workload == "clip-only"
-    unet = None if clip_only else create_unet(size if size in (256, 512) else 512, seed=2, device=dev, use_fp16=True)
+    unet = None if clip_only else create_unet(size if size in (256, 512) else 512, seed=2, device=dev, use_fp16=True, channels_last=args.unet_layout == "nhwc")
     diffusion = SpacedDiffusion(steps=ddim)
     unet_graphed = False
     if unet is not None and not args.no_graphs and not args.two_forwards:
@@ -338,7 +340,7 @@ def main():
     line = {
         "metric": METRIC % (size, size), "value": cuts_per_step * value, "unit": "cutouts/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": desc, "cutouts_per_step": cuts_per_step, "cutouts_per_rank": -(-cuts_per_step // world), "unet_cuda_graphs": unet_graphed, "unet": "fp16 stock PyTorch, replicated; %s" % ("two forwards per step (sampler + cond_fn) like the reference" if args.two_forwards else "one grad-enabled forward shared by sampler and cond_fn (identical results)"),
+        "config": {"workload": desc, "cutouts_per_step": cuts_per_step, "cutouts_per_rank": -(-cuts_per_step // world), "unet_cuda_graphs": unet_graphed, "unet": "fp16, replicated, %s; %s" % ("channels_last cuDNN convs + fused NHWC GroupNorm/scale-shift/SiLU kernels" if args.unet_layout == "nhwc" else "NCHW stock PyTorch", "two forwards per step (sampler + cond_fn) like the reference" if args.two_forwards else "one grad-enabled forward shared by sampler and cond_fn (identical results)"),
                    "clip": "bf16 operands / fp32 accumulate + fp32 residual stream, random init", "parallelism": "%d cutouts per (model, step) sharded over %d rank(s) = %d per rank, 1 all-reduce of the image gradient per step" % (n_over + n_inner, world, -(-(n_over + n_inner) // world)),
                    "l2": "working set (1.1 GB UNet + ViT weights + activations) far exceeds the 126 MB L2; no flush"},
         "steps_per_s": value,

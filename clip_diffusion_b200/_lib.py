@@ -82,13 +82,16 @@ _SIGNATURES = {
     "cg_any_nan": (_I, [_P, _L, _P, _P]),
     "cg_dynamic_threshold_workspace_bytes": (C.c_size_t, [_I]),
     "cg_dynamic_threshold": (_I, [_P, _I, _L, _F, _F, _P, _P, _P, _P]),
+    "cg_groupnorm_nhwc_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "cg_groupnorm_nhwc_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P]),
+    "cg_groupnorm_nhwc_bwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
 }
 
 _lib = None
 launch_count = 0     # C-ABI calls made through this module
 kernel_launches = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
 # kernels launched per entry point (csrc/*.cu); 1 unless listed
-_KERNELS_PER_CALL = {"cg_cutouts_fwd": 4, "cg_cutouts_bwd": 4, "cg_attention_bwd": 3, "cg_grad_finalize": 2, "cg_any_nan": 2, "cg_dynamic_threshold": 5}
+_KERNELS_PER_CALL = {"cg_cutouts_fwd": 4, "cg_cutouts_bwd": 4, "cg_attention_bwd": 3, "cg_grad_finalize": 2, "cg_any_nan": 2, "cg_dynamic_threshold": 5, "cg_groupnorm_nhwc_fwd": 3, "cg_groupnorm_nhwc_bwd": 3}
 
 
 class ClipGuideError(RuntimeError):

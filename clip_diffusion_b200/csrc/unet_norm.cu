@@ -1,0 +1,451 @@
+// Fused GroupNorm32 (+ scale-shift) (+ SiLU) forward / input-gradient for the NHWC fp16 activations of the replicated
+// guided-diffusion UNet (the UNet is built at clip_diffusion/models.py:87-131, its blocks are
+// restated in App. A.3: ResBlock = GN32 -> SiLU -> conv, GN32 -> *(1+scale)+shift -> SiLU -> conv; AttentionBlock = GN32 -> qkv).
+//
+// Why: after the CLIP side ran on tensor cores, a 512x512 guidance step spent ~25 of 60 ms in stock element-wise kernels
+// around cuDNN (NCHW<->NHWC transposes 10 ms, addcmul 7.6 ms, Welford/sum reductions 5 ms, SiLU fwd/bwd 2 ms ...;
+// profiles/r01_c2_step_kernel_table_*).  Keeping the trunk NHWC removes the transposes, and these kernels make every
+// normalisation 3 (forward) / 5 (backward) HBM passes over the activation instead of 10-14:
+//
+//   forward : partial (per-channel sum / sum of squares per row chunk)  ->  finalize (mean, rstd per group in fp64, per-channel
+//             affine a_c, b_c with gamma/beta and the timestep scale-shift folded in)  ->  apply y = act(a_c*x + b_c)
+//   backward: partial (per-channel sum dv and sum dv*x, dv = dy*silu'(a_c*x+b_c) recomputed)  ->  finalize (per-group B, C)
+//             ->  apply dx = a_c*dv + B_g*x + C_g
+//
+// All three are HBM-bound streaming kernels: 128-bit loads of 8 channels per thread, a thread keeps ONE channel octet for
+// its whole life (coefficients live in registers), rows are split into chunks so the grid is ~4 CTAs per SM for the large
+// levels, four independent loads in flight per thread.  No atomics: partials are reduced in a fixed order => deterministic.
+// Weights are frozen (models.py:120-127 only re-enables grads that never reach the sampler state) => no dgamma/dbeta.
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxThreads = 256;
+constexpr int kUnroll = 4;
+
+struct Geo {
+  int cvecs;           // C / 8: channel octets per row
+  int rows_per_iter;   // rows a CTA covers per loop iteration
+  int threads;         // cvecs * rows_per_iter  (<= 256)
+  int chunks;          // row chunks per sample (gridDim.x)
+  int rows_per_chunk;
+};
+
+static Geo geometry(int N, int HW, int C) {
+  Geo g;
+  g.cvecs = C / 8;
+  g.rows_per_iter = kMaxThreads / g.cvecs;
+  if (g.rows_per_iter < 1) g.rows_per_iter = 1;
+  g.threads = g.cvecs * g.rows_per_iter;
+  int target = (4 * CG_NUM_SMS) / (N > 0 ? N : 1);
+  if (target < 1) target = 1;
+  const int min_rows = g.rows_per_iter * kUnroll;
+  int max_chunks = HW / min_rows;
+  if (max_chunks < 1) max_chunks = 1;
+  int chunks = target < max_chunks ? target : max_chunks;
+  g.rows_per_chunk = (HW + chunks - 1) / chunks;
+  g.chunks = (HW + g.rows_per_chunk - 1) / g.rows_per_chunk;
+  return g;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+  return u;
+}
+
+// sigmoid(v) = 0.5*tanh(0.5 v) + 0.5 : one MUFU instead of exp + rcp (the kernels must stay HBM-bound, not MUFU-bound)
+__device__ __forceinline__ float sigmoid_fast(float v) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+  return fmaf(0.5f, t, 0.5f);
+}
+
+template <typename T>
+struct Row8;  // 8 consecutive channels of one pixel
+template <>
+struct Row8<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float* f) { unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f); }
+  static __device__ __forceinline__ void zero_or_load(const __half* p, bool ok, float* f) {
+    if (ok) load(p, f);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float* f) { *reinterpret_cast<uint4*>(p) = pack8(f); }
+};
+template <>
+struct Row8<float> {
+  static __device__ __forceinline__ void load(const float* p, float* f) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  static __device__ __forceinline__ void zero_or_load(const float* p, bool ok, float* f) {
+    if (ok) load(p, f);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    }
+  }
+  static __device__ __forceinline__ void store(float* p, const float* f) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
+__device__ __forceinline__ void load_coef8(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// Reduce the per-thread octet accumulators of the CTA's rows_per_iter row lanes and write one (s0, s1) pair per channel.
+__device__ __forceinline__ void reduce_rows_and_store(const float* s0, const float* s1, int C, int cvecs, int rows_per_iter, float* red /*[2][2048]*/,
+                                                      float2* __restrict__ out /*[C]*/) {
+  const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
+  float* r0 = red + r * C + col * 8;
+  float* r1 = red + 2048 + r * C + col * 8;
+  reinterpret_cast<float4*>(r0)[0] = make_float4(s0[0], s0[1], s0[2], s0[3]);
+  reinterpret_cast<float4*>(r0)[1] = make_float4(s0[4], s0[5], s0[6], s0[7]);
+  reinterpret_cast<float4*>(r1)[0] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+  reinterpret_cast<float4*>(r1)[1] = make_float4(s1[4], s1[5], s1[6], s1[7]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < rows_per_iter; ++k) {
+      a += red[k * C + c];
+      b += red[2048 + k * C + c];
+    }
+    out[c] = make_float2(a, b);
+  }
+}
+
+// ---- forward -----------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kMaxThreads) gn_stats_partial_kernel(const __half* __restrict__ x, int HW, int C, int cvecs, int rows_per_iter,
+                                                                        int rows_per_chunk, float2* __restrict__ partial) {
+  __shared__ __align__(16) float red[2 * 2048];
+  const int n = blockIdx.y, p = blockIdx.x;
+  const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
+  const int row_end = min(HW, (p + 1) * rows_per_chunk);
+  const __half* base = x + (size_t)n * HW * C + col * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (int row = p * rows_per_chunk + r; row < row_end; row += kUnroll * rows_per_iter) {
+    float v[kUnroll][8];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const int rr = row + k * rows_per_iter;
+      Row8<__half>::zero_or_load(base + (size_t)rr * C, rr < row_end, v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[k][j];
+        q[j] = fmaf(v[k][j], v[k][j], q[j]);
+      }
+  }
+  reduce_rows_and_store(s, q, C, cvecs, rows_per_iter, red, partial + ((size_t)n * gridDim.x + p) * C);
+}
+
+__device__ __forceinline__ double block_sum_f64(double v, double* red /*>=32*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double t = 0.0;
+  for (int k = 0; k < nw; ++k) t += red[k];
+  return t;
+}
+
+// one CTA per (sample, group): statistics in fp64 from the chunk partials, then the per-channel affine of the whole
+// normalisation: y = act(a_c * x + b_c),  a_c = rstd*gamma_c*(1+scale_c),  b_c = (beta_c - mean*rstd*gamma_c)*(1+scale_c) + shift_c
+__global__ void __launch_bounds__(128) gn_finalize_fwd_kernel(const float2* __restrict__ partial, int chunks, int C, int G, int HW,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const float* __restrict__ scale_shift, float eps, float* __restrict__ stats,
+                                                               float* __restrict__ coefA, float* __restrict__ coefB) {
+  __shared__ double red[32];
+  const int n = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
+  double s = 0.0, q = 0.0;
+  for (int idx = threadIdx.x; idx < chunks * cg; idx += blockDim.x) {
+    const int p = idx / cg, cc = idx - p * cg;
+    const float2 v = partial[((size_t)n * chunks + p) * C + g * cg + cc];
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+  s = block_sum_f64(s, red);
+  q = block_sum_f64(q, red);
+  const double m = (double)HW * (double)cg;
+  const double mean = s / m;
+  double var = q / m - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float meanf = (float)mean;
+  if (threadIdx.x == 0) {
+    stats[2 * blockIdx.x] = meanf;
+    stats[2 * blockIdx.x + 1] = rstd;
+  }
+  for (int cc = threadIdx.x; cc < cg; cc += blockDim.x) {
+    const int c = g * cg + cc;
+    float a = gamma[c] * rstd;
+    float b = beta[c] - meanf * a;
+    if (scale_shift) {
+      // the reference casts the embedding projection to the activation dtype first (`.type(h.dtype)`, guided-diffusion ResBlock)
+      const float sc = 1.f + __half2float(__float2half_rn(scale_shift[(size_t)n * 2 * C + c]));
+      const float sh = __half2float(__float2half_rn(scale_shift[(size_t)n * 2 * C + C + c]));
+      a *= sc;
+      b = fmaf(b, sc, sh);
+    }
+    coefA[(size_t)n * C + c] = a;
+    coefB[(size_t)n * C + c] = b;
+  }
+}
+
+template <bool SILU, typename TOut>
+__global__ void __launch_bounds__(kMaxThreads) gn_apply_fwd_kernel(const __half* __restrict__ x, int HW, int C, int cvecs, int rows_per_iter,
+                                                                    int rows_per_chunk, const float* __restrict__ coefA,
+                                                                    const float* __restrict__ coefB, TOut* __restrict__ y) {
+  const int n = blockIdx.y, p = blockIdx.x;
+  const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
+  const int row_end = min(HW, (p + 1) * rows_per_chunk);
+  float a[8], b[8];
+  load_coef8(coefA + (size_t)n * C + col * 8, a);
+  load_coef8(coefB + (size_t)n * C + col * 8, b);
+  const size_t off = (size_t)n * HW * C + col * 8;
+  for (int row = p * rows_per_chunk + r; row < row_end; row += kUnroll * rows_per_iter) {
+    float v[kUnroll][8];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const int rr = row + k * rows_per_iter;
+      Row8<__half>::zero_or_load(x + off + (size_t)rr * C, rr < row_end, v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const int rr = row + k * rows_per_iter;
+      if (rr < row_end) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float u = fmaf(a[j], v[k][j], b[j]);
+          v[k][j] = SILU ? u * sigmoid_fast(u) : u;
+        }
+        Row8<TOut>::store(y + off + (size_t)rr * C, v[k]);
+      }
+    }
+  }
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------------
+
+template <bool SILU>
+__device__ __forceinline__ float dact(float dy, float u) {
+  if (!SILU) return dy;
+  const float sg = sigmoid_fast(u);
+  return dy * sg * fmaf(u, 1.f - sg, 1.f);  // silu'(u) = s(u) * (1 + u*(1 - s(u)))
+}
+
+template <bool SILU, typename TDy>
+__global__ void __launch_bounds__(kMaxThreads) gn_bwd_partial_kernel(const TDy* __restrict__ dy, const __half* __restrict__ x, int HW, int C, int cvecs,
+                                                                      int rows_per_iter, int rows_per_chunk, const float* __restrict__ coefA,
+                                                                      const float* __restrict__ coefB, float2* __restrict__ partial) {
+  __shared__ __align__(16) float red[2 * 2048];
+  const int n = blockIdx.y, p = blockIdx.x;
+  const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
+  const int row_end = min(HW, (p + 1) * rows_per_chunk);
+  float a[8], b[8];
+  if (SILU) {
+    load_coef8(coefA + (size_t)n * C + col * 8, a);
+    load_coef8(coefB + (size_t)n * C + col * 8, b);
+  }
+  const size_t off = (size_t)n * HW * C + col * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  constexpr int U = 2;  // two (dy, x) row pairs in flight: same bytes in flight as the forward's four
+  for (int row = p * rows_per_chunk + r; row < row_end; row += U * rows_per_iter) {
+    float xv[U][8], gv[U][8];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int rr = row + k * rows_per_iter;
+      Row8<__half>::zero_or_load(x + off + (size_t)rr * C, rr < row_end, xv[k]);
+      Row8<TDy>::zero_or_load(dy + off + (size_t)rr * C, rr < row_end, gv[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dv = dact<SILU>(gv[k][j], SILU ? fmaf(a[j], xv[k][j], b[j]) : 0.f);
+        s1[j] += dv;
+        s2[j] = fmaf(dv, xv[k][j], s2[j]);
+      }
+  }
+  reduce_rows_and_store(s1, s2, C, cvecs, rows_per_iter, red, partial + ((size_t)n * gridDim.x + p) * C);
+}
+
+// with w_c = a_c / rstd (= gamma_c*(1+scale_c)), x^ = (x-mean)*rstd and dx^ = w_c*dv:
+//   dx = rstd*(dx^ - mean_g(dx^) - x^ * mean_g(dx^ x^)) = a_c*dv + B_g*x + C_g
+__global__ void __launch_bounds__(128) gn_finalize_bwd_kernel(const float2* __restrict__ partial, int chunks, int C, int G, int HW,
+                                                               const float* __restrict__ stats, const float* __restrict__ coefA,
+                                                               float* __restrict__ coefBx, float* __restrict__ coefCx) {
+  __shared__ double red[32];
+  const int n = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
+  const float mean = stats[2 * blockIdx.x], rstd = stats[2 * blockIdx.x + 1];
+  double t1 = 0.0, t2 = 0.0;
+  for (int idx = threadIdx.x; idx < chunks * cg; idx += blockDim.x) {
+    const int p = idx / cg, cc = idx - p * cg;
+    const int c = g * cg + cc;
+    const float2 v = partial[((size_t)n * chunks + p) * C + c];
+    const double w = (double)coefA[(size_t)n * C + c] / (double)rstd;
+    t1 += w * (double)v.x;
+    t2 += w * (double)v.y;
+  }
+  t1 = block_sum_f64(t1, red);
+  t2 = block_sum_f64(t2, red);
+  const double m = (double)HW * (double)cg;
+  const double c1 = t1 / m;
+  const double c2 = (double)rstd * (t2 - (double)mean * t1) / m;
+  const double Bg = -(double)rstd * (double)rstd * c2;
+  const double Cg = -(double)rstd * c1 - Bg * (double)mean;
+  for (int cc = threadIdx.x; cc < cg; cc += blockDim.x) {
+    coefBx[(size_t)n * C + g * cg + cc] = (float)Bg;
+    coefCx[(size_t)n * C + g * cg + cc] = (float)Cg;
+  }
+}
+
+template <bool SILU, typename TDy>
+__global__ void __launch_bounds__(kMaxThreads) gn_apply_bwd_kernel(const TDy* __restrict__ dy, const __half* __restrict__ x, int HW, int C, int cvecs,
+                                                                    int rows_per_iter, int rows_per_chunk, const float* __restrict__ coefA,
+                                                                    const float* __restrict__ coefB, const float* __restrict__ coefBx,
+                                                                    const float* __restrict__ coefCx, __half* __restrict__ dx) {
+  const int n = blockIdx.y, p = blockIdx.x;
+  const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
+  const int row_end = min(HW, (p + 1) * rows_per_chunk);
+  float a[8], b[8], bx[8], cx[8];
+  load_coef8(coefA + (size_t)n * C + col * 8, a);
+  if (SILU) load_coef8(coefB + (size_t)n * C + col * 8, b);
+  load_coef8(coefBx + (size_t)n * C + col * 8, bx);
+  load_coef8(coefCx + (size_t)n * C + col * 8, cx);
+  const size_t off = (size_t)n * HW * C + col * 8;
+  constexpr int U = 2;
+  for (int row = p * rows_per_chunk + r; row < row_end; row += U * rows_per_iter) {
+    float xv[U][8], gv[U][8];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int rr = row + k * rows_per_iter;
+      Row8<__half>::zero_or_load(x + off + (size_t)rr * C, rr < row_end, xv[k]);
+      Row8<TDy>::zero_or_load(dy + off + (size_t)rr * C, rr < row_end, gv[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int rr = row + k * rows_per_iter;
+      if (rr < row_end) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dv = dact<SILU>(gv[k][j], SILU ? fmaf(a[j], xv[k][j], b[j]) : 0.f);
+          gv[k][j] = fmaf(a[j], dv, fmaf(bx[j], xv[k][j], cx[j]));
+        }
+        Row8<__half>::store(dx + off + (size_t)rr * C, gv[k]);
+      }
+    }
+  }
+}
+
+int check_shape(int N, int HW, int C, int G) {
+  CG_REQUIRE(N >= 1 && HW >= 1 && C >= 8 && G >= 1, "groupnorm_nhwc: bad sizes N=%d HW=%d C=%d G=%d", N, HW, C, G);
+  CG_REQUIRE(C % 8 == 0 && C <= 2048, "groupnorm_nhwc: C=%d must be a multiple of 8 and <= 2048", C);
+  CG_REQUIRE(C % G == 0, "groupnorm_nhwc: C=%d not divisible by groups=%d", C, G);
+  CG_REQUIRE(N <= 65535, "groupnorm_nhwc: N=%d too large", N);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t cg_groupnorm_nhwc_workspace_bytes(int N, int HW, int C) {
+  if (N < 1 || HW < 1 || C < 8 || C % 8) return 0;
+  const Geo g = geometry(N, HW, C);
+  // chunk partials (float2 per channel) + the backward's two per-channel coefficient rows
+  return (size_t)N * g.chunks * C * sizeof(float2) + (size_t)2 * N * C * sizeof(float);
+}
+
+extern "C" int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G, const float* gamma, const float* beta, const float* scale_shift,
+                                     float eps, int silu, int out_f32, void* y, float* stats, float* coef, void* workspace, void* stream) {
+  if (int rc = check_shape(N, HW, C, G)) return rc;
+  CG_REQUIRE(x && y && gamma && beta && stats && coef && workspace, "groupnorm_nhwc_fwd: null pointer");
+  CG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)coef & 15) == 0, "groupnorm_nhwc_fwd: buffers must be 16-byte aligned");
+  const Geo g = geometry(N, HW, C);
+  cudaStream_t st = cg_stream(stream);
+  float2* partial = (float2*)workspace;
+  float* coefA = coef;
+  float* coefB = coef + (size_t)N * C;
+  const dim3 grid(g.chunks, N);
+  const __half* xh = (const __half*)x;
+  gn_stats_partial_kernel<<<grid, g.threads, 0, st>>>(xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, partial);
+  CG_LAUNCH_CHECK();
+  gn_finalize_fwd_kernel<<<N * G, 128, 0, st>>>(partial, g.chunks, C, G, HW, gamma, beta, scale_shift, eps, stats, coefA, coefB);
+  CG_LAUNCH_CHECK();
+#define CG_GN_APPLY(S, T) \
+  gn_apply_fwd_kernel<S, T><<<grid, g.threads, 0, st>>>(xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB, (T*)y)
+  if (silu) {
+    if (out_f32) CG_GN_APPLY(true, float);
+    else CG_GN_APPLY(true, __half);
+  } else {
+    if (out_f32) CG_GN_APPLY(false, float);
+    else CG_GN_APPLY(false, __half);
+  }
+#undef CG_GN_APPLY
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, int N, int HW, int C, int G, const float* stats, const float* coef,
+                                     int silu, void* dx, void* workspace, void* stream) {
+  if (int rc = check_shape(N, HW, C, G)) return rc;
+  CG_REQUIRE(dy && x && stats && coef && dx && workspace, "groupnorm_nhwc_bwd: null pointer");
+  CG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+             "groupnorm_nhwc_bwd: buffers must be 16-byte aligned");
+  const Geo g = geometry(N, HW, C);
+  cudaStream_t st = cg_stream(stream);
+  float2* partial = (float2*)workspace;
+  float* coefBx = (float*)(partial + (size_t)N * g.chunks * C);
+  float* coefCx = coefBx + (size_t)N * C;
+  const float* coefA = coef;
+  const float* coefB = coef + (size_t)N * C;
+  const dim3 grid(g.chunks, N);
+  const __half* xh = (const __half*)x;
+#define CG_GN_BWD(S, T)                                                                                                                        \
+  do {                                                                                                                                         \
+    gn_bwd_partial_kernel<S, T><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB, partial); \
+    CG_LAUNCH_CHECK();                                                                                                                         \
+    gn_finalize_bwd_kernel<<<N * G, 128, 0, st>>>(partial, g.chunks, C, G, HW, stats, coefA, coefBx, coefCx);                                  \
+    CG_LAUNCH_CHECK();                                                                                                                         \
+    gn_apply_bwd_kernel<S, T><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB, coefBx, \
+                                                          coefCx, (__half*)dx);                                                                \
+    CG_LAUNCH_CHECK();                                                                                                                         \
+  } while (0)
+  if (silu) {
+    if (dy_f32) CG_GN_BWD(true, float);
+    else CG_GN_BWD(true, __half);
+  } else {
+    if (dy_f32) CG_GN_BWD(false, float);
+    else CG_GN_BWD(false, __half);
+  }
+#undef CG_GN_BWD
+  return 0;
+}

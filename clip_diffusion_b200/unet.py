@@ -84,10 +84,32 @@ class _SplitStatsGroupNorm(torch.autograd.Function):
 
 
 class GroupNorm32(nn.GroupNorm):
-    def forward(self, x):
+    """guided-diffusion's GroupNorm32 (fp32 statistics) with the block's follow-up element-wise work as arguments:
+    ``forward(x, scale_shift=None, silu=False)`` = ``act(GN(x) * (1 + scale) + shift)``.
+
+    ``nhwc`` (set by ``create_unet(channels_last=True)``): fp16 CUDA activations go through ONE fused sm_100a op
+    (clip_diffusion_b200.unet_ops / csrc/unet_norm.cu); otherwise the same arithmetic is spelled in stock torch ops (the CPU
+    fp32 model of the oracle / reference arm, and the NCHW fp16 variant kept for A/B measurements)."""
+
+    nhwc = False
+
+    def forward(self, x, scale_shift=None, silu=False, out_dtype=None):
+        if self.nhwc and x.is_cuda and x.dtype == torch.float16:
+            from clip_diffusion_b200.unet_ops import group_norm_nhwc
+
+            if x.dim() == 4 and not x.is_contiguous(memory_format=torch.channels_last):
+                x = x.contiguous(memory_format=torch.channels_last)
+            return group_norm_nhwc(x, self.weight, self.bias, self.num_groups, self.eps, scale_shift=scale_shift, silu=silu, out_dtype=out_dtype)
         if x.is_cuda and x.dtype == torch.float16:
-            return _SplitStatsGroupNorm.apply(x, self.weight, self.bias, self.num_groups, self.eps)
-        return super().forward(x.float()).type(x.dtype)  # guided-diffusion's GroupNorm32 (fp32 statistics)
+            y = _SplitStatsGroupNorm.apply(x, self.weight, self.bias, self.num_groups, self.eps)
+        else:
+            y = super().forward(x.float()).type(x.dtype)
+        if scale_shift is not None:
+            scale, shift = scale_shift.type(y.dtype)[:, :, None, None].chunk(2, dim=1)
+            y = y * (1 + scale) + shift
+        if silu:
+            y = F.silu(y)
+        return y if out_dtype is None else y.type(out_dtype)
 
 
 def timestep_embedding(timesteps, dim, max_period=10000):
@@ -119,14 +141,13 @@ class ResBlock(nn.Module):
         self.skip = nn.Identity() if out_channels == channels else nn.Conv2d(channels, out_channels, 1)
 
     def forward(self, x, emb):
-        h = F.silu(self.in_norm(x))
+        h = self.in_norm(x, silu=True)
         if self.resample is not None:
             h = self.resample(h)
             x = self.resample(x)
         h = self.in_conv(h)
-        scale, shift = self.emb(F.silu(emb)).type(h.dtype)[:, :, None, None].chunk(2, dim=1)
-        h = self.out_norm(h) * (1 + scale) + shift
-        h = self.out_conv(F.silu(h))
+        h = self.out_norm(h, scale_shift=self.emb(F.silu(emb)), silu=True)  # scale-shift norm: GN(h) * (1 + scale) + shift
+        h = self.out_conv(h)
         return self.skip(x) + h
 
 
@@ -140,6 +161,8 @@ class AttentionBlock(nn.Module):
 
     def forward(self, x):
         b, c, hh, ww = x.shape
+        if self.norm.nhwc and x.is_cuda and x.dtype == torch.float16:
+            return self._forward_nhwc(x)
         xf = x.reshape(b, c, -1)
         qkv = self.qkv(self.norm(xf))  # [b, 3c, t], legacy order: heads x (q|k|v) x head_dim
         t = qkv.shape[-1]
@@ -147,6 +170,20 @@ class AttentionBlock(nn.Module):
         a = F.scaled_dot_product_attention(q.transpose(1, 2).unsqueeze(0), k.transpose(1, 2).unsqueeze(0), v.transpose(1, 2).unsqueeze(0))
         a = a.squeeze(0).transpose(1, 2).reshape(b, c, t)
         return (xf + self.proj(a)).reshape(b, c, hh, ww)
+
+    def _forward_nhwc(self, x):
+        """Same block on channels_last activations: NHWC memory IS the token-major [t, c] matrix, so the 1x1 convolutions are
+        plain linears on a view and nothing is transposed.  Legacy qkv channel order: heads x (q|k|v) x head_dim."""
+        b, c, hh, ww = x.shape
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        t = hh * ww
+        tok = x.permute(0, 2, 3, 1).reshape(b, t, c)  # a view
+        qkv = F.linear(self.norm(tok), self.qkv.weight.squeeze(-1), self.qkv.bias)
+        q, k, v = qkv.view(b, t, self.heads, 3, c // self.heads).permute(3, 0, 2, 1, 4)
+        a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, t, c)
+        out = tok + F.linear(a, self.proj.weight.squeeze(-1), self.proj.bias)
+        return out.view(b, hh, ww, c).permute(0, 3, 1, 2)
 
 
 class _Seq(nn.Module):
@@ -230,8 +267,11 @@ class UNetModel(nn.Module):
         h = self.middle_block(h, emb)
         for blk in self.output_blocks:
             h = blk(torch.cat([h, hs.pop()], dim=1), emb)
-        h = h.type(x.dtype)
-        return self.out_conv(F.silu(self.out_norm(h)))
+        if self.channels_last and h.is_cuda and h.dtype == torch.float16:
+            h = self.out_norm(h, silu=True, out_dtype=x.dtype)  # fp32 statistics and fp32 output from the fp16 trunk, one pass
+        else:
+            h = self.out_norm(h.type(x.dtype), silu=True)
+        return self.out_conv(h)
 
 
 def create_unet(image_size=512, seed=2, device="cuda", use_fp16=True, config=None, channels_last=None):
@@ -242,9 +282,16 @@ def create_unet(image_size=512, seed=2, device="cuda", use_fp16=True, config=Non
         torch.manual_seed(seed)
         model = UNetModel(image_size, use_fp16=use_fp16, config=config)
     model = model.to(device).eval().requires_grad_(False)
-    if channels_last:  # cuDNN's tensor-core convolutions are NHWC: keep everything NHWC instead of transposing around each conv
+    if channels_last is None:
+        channels_last = use_fp16 and torch.device(device).type == "cuda"
+    if channels_last:
+        # cuDNN's tensor-core convolutions are NHWC: keep the whole trunk NHWC instead of transposing around every conv, with the
+        # normalisation / activation work between the convs in fused NHWC kernels (unet_ops.group_norm_nhwc)
         model = model.to(memory_format=torch.channels_last)
         model.channels_last = True
+        for mod in model.modules():
+            if isinstance(mod, GroupNorm32):
+                mod.nhwc = True
     return model
 
 

@@ -1,0 +1,77 @@
+"""Fused NHWC GroupNorm32 (+ scale-shift) (+ SiLU) for the replicated guided-diffusion UNet, over csrc/unet_norm.cu.
+
+SURVEY.md section 8(f) N1: once the CLIP side runs on tensor cores the guidance step is dominated by the element-wise
+traffic of the stock-PyTorch UNet around cuDNN's NHWC convolutions.  `group_norm_nhwc` is one op for what the reference's
+ResBlock spells `silu(GroupNorm32(x))` / `silu(GroupNorm32(h) * (1 + scale) + shift)` (un-vendored guided-diffusion,
+App. A.3) on channels_last fp16 tensors; its autograd backward yields the input gradient only (UNet weights are frozen).
+No fallback: a missing library raises (see _lib.load).
+"""
+import torch
+
+from clip_diffusion_b200 import _lib
+
+
+def _nhwc_dims(x):
+    """(N, HW, C) of a tensor whose memory is [N, spatial..., C] row-major: 4-D channels_last or 3-D [N, T, C] contiguous."""
+    if x.dim() == 4:
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            raise _lib.ClipGuideError("group_norm_nhwc: 4-D input must be channels_last contiguous")
+        return x.shape[0], x.shape[2] * x.shape[3], x.shape[1]
+    if x.dim() == 3:
+        if not x.is_contiguous():
+            raise _lib.ClipGuideError("group_norm_nhwc: 3-D input must be [N, T, C] contiguous")
+        return x.shape[0], x.shape[1], x.shape[2]
+    raise _lib.ClipGuideError("group_norm_nhwc: expected [N,C,H,W] channels_last or [N,T,C]; got %s" % (tuple(x.shape),))
+
+
+def _like_layout(x, t):
+    """Bring a gradient to the memory layout of x (autograd may hand back NCHW-contiguous or expanded tensors)."""
+    if x.dim() == 4:
+        return t.contiguous(memory_format=torch.channels_last)
+    return t.contiguous()
+
+
+class _GroupNormNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, silu, out_f32):
+        _lib.require_cuda(x, gamma, beta, scale_shift)
+        if x.dtype != torch.float16:
+            raise _lib.ClipGuideError("group_norm_nhwc: fp16 activations expected, got %s" % x.dtype)
+        N, HW, C = _nhwc_dims(x)
+        gamma = gamma.detach().float().contiguous()
+        beta = beta.detach().float().contiguous()
+        if scale_shift is not None:
+            scale_shift = scale_shift.detach().float().contiguous()
+            if tuple(scale_shift.shape) != (N, 2 * C):
+                raise ValueError("scale_shift must be [N, 2C] = %s, got %s" % ((N, 2 * C), tuple(scale_shift.shape)))
+        y = torch.empty_like(x, dtype=torch.float32 if out_f32 else torch.float16)  # preserve_format: same NHWC strides
+        stats = torch.empty(N, groups, 2, device=x.device, dtype=torch.float32)
+        coef = torch.empty(2, N, C, device=x.device, dtype=torch.float32)
+        ws = torch.empty(_lib.load().cg_groupnorm_nhwc_workspace_bytes(N, HW, C), device=x.device, dtype=torch.uint8)
+        _lib.call("cg_groupnorm_nhwc_fwd", _lib.ptr(x), N, HW, C, int(groups), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(scale_shift),
+                  float(eps), int(bool(silu)), int(bool(out_f32)), _lib.ptr(y), _lib.ptr(stats), _lib.ptr(coef), _lib.ptr(ws))
+        ctx.save_for_backward(x, stats, coef)
+        ctx.cfg = (N, HW, C, int(groups), int(bool(silu)), bool(out_f32))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, coef = ctx.saved_tensors
+        N, HW, C, groups, silu, out_f32 = ctx.cfg
+        dy = _like_layout(x, dy)
+        if dy.dtype not in (torch.float16, torch.float32):
+            dy = dy.float()
+        dx = torch.empty_like(x)
+        ws = torch.empty(_lib.load().cg_groupnorm_nhwc_workspace_bytes(N, HW, C), device=x.device, dtype=torch.uint8)
+        _lib.call("cg_groupnorm_nhwc_bwd", _lib.ptr(dy), int(dy.dtype == torch.float32), _lib.ptr(x), N, HW, C, groups, _lib.ptr(stats),
+                  _lib.ptr(coef), silu, _lib.ptr(dx), _lib.ptr(ws))
+        return dx, None, None, None, None, None, None, None
+
+
+def group_norm_nhwc(x, gamma, beta, groups=32, eps=1e-5, scale_shift=None, silu=False, out_dtype=None):
+    """act(GroupNorm32(x) * (1 + scale) + shift) for x [N,C,H,W] channels_last (or [N,T,C]) fp16 on CUDA.
+
+    scale_shift: [N, 2C] (the ResBlock's embedding projection, scale | shift) or None; silu: apply SiLU;
+    out_dtype: torch.float16 (default) or torch.float32 (the UNet's fp32 output head)."""
+    out_f32 = out_dtype == torch.float32
+    return _GroupNormNHWC.apply(x, gamma, beta, scale_shift, groups, eps, silu, out_f32)

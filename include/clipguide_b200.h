@@ -184,6 +184,22 @@ size_t cg_dynamic_threshold_workspace_bytes(int B);
 int cg_dynamic_threshold(const float* x, int B, int64_t n, float q, float min_thr, float* out, float* thr_out, void* workspace,
                          void* stream);
 
+/* ------------------------------------------------------------------ replicated UNet (next row N1) ---- */
+/* GroupNorm32 (+ timestep scale-shift) (+ SiLU) of the guided-diffusion UNet blocks (built at clip_diffusion/models.py:87-131;
+ * ResBlock / AttentionBlock of the un-vendored crowsonkb/guided-diffusion), for NHWC fp16 activations:
+ *   y[n,p,c] = act( (gamma_c * (x - mean_{n,g}) * rstd_{n,g} + beta_c) * (1 + scale[n,c]) + shift[n,c] )
+ * x [N,HW,C] fp16 (channels_last), C % 8 == 0, C <= 2048, C % G == 0; gamma, beta [C] fp32; scale_shift [N,2C] fp32 (scale | shift)
+ * or NULL; act = SiLU if silu != 0; y [N,HW,C] fp16 (out_f32 == 0) or fp32.  Statistics in fp32/fp64 like GroupNorm32's x.float().
+ * stats [N,G,2] (mean, rstd) and coef [2,N,C] (the folded per-channel affine a_c, b_c) are outputs kept for the backward.
+ * workspace: cg_groupnorm_nhwc_workspace_bytes(N,HW,C) bytes, 16-byte aligned. */
+size_t cg_groupnorm_nhwc_workspace_bytes(int N, int HW, int C);
+int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G, const float* gamma, const float* beta, const float* scale_shift,
+                          float eps, int silu, int out_f32, void* y, float* stats, float* coef, void* workspace, void* stream);
+/* input gradient of the above (weights are frozen, models.py:67-71 / :120-127): dy [N,HW,C] fp16 (dy_f32 == 0) or fp32,
+ * x / stats / coef as given to / produced by the forward -> dx [N,HW,C] fp16. */
+int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, int N, int HW, int C, int G, const float* stats, const float* coef,
+                          int silu, void* dx, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,25 @@ def test_diffusion_schedule_and_unet():
     assert abs(n512 / 1e6 - 558.0) < 0.1 and abs(n256 / 1e6 - 552.8) < 0.1  # SURVEY.md App. A.3 parameter counts
 
 
+def test_group_norm32_stock_path_spells_the_resblock_arithmetic():
+    """GroupNorm32(x, scale_shift, silu) on the CPU / fp32 path == silu(GN(x) * (1 + scale) + shift) (guided-diffusion ResBlock)."""
+    from torch.nn import functional as Fn
+
+    from clip_diffusion_b200.unet import GroupNorm32
+
+    g = torch.Generator().manual_seed(0)
+    gn = GroupNorm32(4, 16)
+    with torch.no_grad():
+        gn.weight.copy_(torch.randn(16, generator=g))
+        gn.bias.copy_(torch.randn(16, generator=g))
+    x = torch.randn(2, 16, 5, 7, generator=g)
+    ss = torch.randn(2, 32, generator=g)
+    want = Fn.group_norm(x, 4, gn.weight, gn.bias, gn.eps)
+    assert torch.allclose(gn(x), want, atol=1e-6)
+    want = Fn.silu(want * (1 + ss[:, :16, None, None]) + ss[:, 16:, None, None])
+    assert torch.allclose(gn(x, scale_shift=ss, silu=True), want, atol=1e-6)
+
+
 def test_ms_ssim_restatement_properties():
     """losses.ms_ssim (restated pytorch_msssim.MS_SSIM, parity unpinned): identity, symmetry, monotone in noise, differentiable."""
     from clip_diffusion_b200.losses import ms_ssim, structural_dissimilarity_loss

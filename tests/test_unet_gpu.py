@@ -1,0 +1,155 @@
+"""GPU parity of the fused NHWC GroupNorm32(+scale-shift)(+SiLU) op (csrc/unet_norm.cu, through the C ABI) against a plain
+PyTorch fp32 reference of the same arithmetic, and of the channels_last UNet built on it against the fp32 model.
+The blocks it serves are guided-diffusion's ResBlock / AttentionBlock (built at clip_diffusion/models.py:87-131)."""
+import copy
+
+import pytest
+import torch
+from torch.nn import functional as F
+
+pytestmark = pytest.mark.gpu
+
+# fp16 input/output (2^-11 rounding) + tanh.approx sigmoid (2^-11): stated tolerances
+TOL_FWD = 2e-3   # relative L2 of y
+TOL_BWD = 3e-3   # relative L2 of dx
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _reference(x_nchw_f32, gamma, beta, groups, eps, scale_shift, silu):
+    y = F.group_norm(x_nchw_f32, groups, gamma, beta, eps)
+    if scale_shift is not None:
+        scale, shift = scale_shift.half().float()[:, :, None, None].chunk(2, dim=1)  # the reference rounds the projection to fp16 first
+        y = y * (1 + scale) + shift
+    return F.silu(y) if silu else y
+
+
+CASES = [
+    # N, C, H, W, groups
+    (1, 128, 64, 64, 32),    # level-0 shape family (cg = 4)
+    (1, 384, 24, 40, 32),    # concat width 256+128: C/8 = 48 does not divide 256 threads
+    (2, 32, 16, 16, 32),     # cg = 1 (test-size UNet), batch 2
+    (1, 64, 7, 9, 32),       # ragged H*W, cg = 2
+    (1, 2048, 8, 8, 32),     # deepest concat: one row lane per CTA
+    (1, 1536, 16, 16, 32),   # C/8 = 192
+    (3, 256, 33, 31, 32),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("silu", [False, True])
+@pytest.mark.parametrize("with_ss", [False, True])
+@pytest.mark.parametrize("out_f32", [False, True])
+def test_group_norm_nhwc_forward_backward(case, silu, with_ss, out_f32):
+    from clip_diffusion_b200.unet_ops import group_norm_nhwc
+
+    N, C, H, W, G = case
+    g = torch.Generator().manual_seed(N * 1000 + C + H)
+    x = (torch.randn(N, C, H, W, generator=g) * 1.5 + 0.7 * torch.randn(1, C, 1, 1, generator=g)).half()
+    gamma = 1 + 0.3 * torch.randn(C, generator=g)
+    beta = 0.2 * torch.randn(C, generator=g)
+    ss = 0.3 * torch.randn(N, 2 * C, generator=g) if with_ss else None
+    dy = torch.randn(N, C, H, W, generator=g)
+    if not out_f32:
+        dy = dy.half()
+
+    xr = x.float().cuda().requires_grad_()
+    yr = _reference(xr, gamma.cuda(), beta.cuda(), G, 1e-5, None if ss is None else ss.cuda(), silu)
+    (dxr,) = torch.autograd.grad(yr, xr, dy.float().cuda())
+
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = group_norm_nhwc(xc, gamma.cuda(), beta.cuda(), G, 1e-5, scale_shift=None if ss is None else ss.cuda(), silu=silu,
+                        out_dtype=torch.float32 if out_f32 else torch.float16)
+    assert y.dtype == (torch.float32 if out_f32 else torch.float16) and y.shape == xc.shape
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    (dx,) = torch.autograd.grad(y, xc, dy.cuda())  # dy arrives NCHW-contiguous: the op re-lays it out
+    assert dx.dtype == torch.float16 and torch.isfinite(dx).all()
+    assert _rel(y.float(), yr) <= TOL_FWD, _rel(y.float(), yr)
+    assert _rel(dx.float(), dxr) <= TOL_BWD, _rel(dx.float(), dxr)
+
+
+def test_group_norm_nhwc_tokens_and_determinism():
+    """[N,T,C] token layout (AttentionBlock) and run-to-run bit-identical results (fixed-order reductions, no atomics)."""
+    from clip_diffusion_b200.unet_ops import group_norm_nhwc
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 1024, 512, generator=g).half().cuda()
+    gamma, beta = torch.rand(512, generator=g).cuda(), torch.rand(512, generator=g).cuda()
+    y0 = group_norm_nhwc(x, gamma, beta, 32, 1e-5)
+    y1 = group_norm_nhwc(x, gamma, beta, 32, 1e-5)
+    assert torch.equal(y0, y1)
+    ref = F.group_norm(x.float().transpose(1, 2), 32, gamma, beta, 1e-5).transpose(1, 2)
+    assert _rel(y0.float(), ref) <= TOL_FWD
+
+
+def test_group_norm_nhwc_large_mean_and_big_plane():
+    """Full-resolution level-0 plane (512x512x128, 67 MB) with a large common offset: fp64 merge of fp32 chunk sums keeps the
+    variance accurate (E[x^2]-mean^2 cancellation)."""
+    from clip_diffusion_b200.unet_ops import group_norm_nhwc
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.randn(1, 128, 512, 512, device="cuda", generator=g) * 0.5 + 6.0).half().contiguous(memory_format=torch.channels_last)
+    gamma, beta = torch.ones(128, device="cuda"), torch.zeros(128, device="cuda")
+    y = group_norm_nhwc(x, gamma, beta, 32, 1e-5)
+    ref = F.group_norm(x.float(), 32, gamma, beta, 1e-5)
+    assert _rel(y.float(), ref) <= TOL_FWD
+
+
+def test_group_norm_nhwc_rejects_bad_input():
+    from clip_diffusion_b200 import _lib
+    from clip_diffusion_b200.unet_ops import group_norm_nhwc
+
+    w = torch.ones(12, device="cuda")
+    with pytest.raises(_lib.ClipGuideError):
+        group_norm_nhwc(torch.zeros(1, 12, 4, 4, device="cuda").half().contiguous(memory_format=torch.channels_last), w, w, 4)  # C % 8
+    with pytest.raises(_lib.ClipGuideError):
+        group_norm_nhwc(torch.zeros(1, 16, 4, 4).half(), torch.ones(16), torch.ones(16), 4)  # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("size", [64, 32])
+def test_unet_nhwc_matches_fp32_model(size):
+    """channels_last fp16 UNet on the fused ops vs the same weights in fp32 stock PyTorch: epsilon and d(sum eps*w)/dx."""
+    from clip_diffusion_b200.unet import create_unet
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ref = create_unet(size, seed=2, device="cpu", use_fp16=False)
+    mine = create_unet(size, seed=2, device="cuda", use_fp16=True)       # default: channels_last + fused norm ops
+    stock = create_unet(size, seed=2, device="cuda", use_fp16=True, channels_last=False)
+    assert mine.channels_last and not stock.channels_last
+    ref = copy.deepcopy(ref).cuda()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 3, 2 * size, 2 * size, generator=g).cuda()
+    w = torch.randn(1, 6, 2 * size, 2 * size, generator=g).cuda()
+    t = torch.tensor([412.0], device="cuda")
+    outs = {}
+    for name, m in (("ref", ref), ("mine", mine), ("stock", stock)):
+        xi = x.clone().requires_grad_()
+        eps = m(xi, t)
+        (gx,) = torch.autograd.grad((eps.float() * w).sum(), xi)
+        outs[name] = (eps.float(), gx.float())
+    e_mine, e_stock = _rel(outs["mine"][0], outs["ref"][0]), _rel(outs["stock"][0], outs["ref"][0])
+    g_mine, g_stock = _rel(outs["mine"][1], outs["ref"][1]), _rel(outs["stock"][1], outs["ref"][1])
+    # fp16 trunk: both variants sit at the fp16 rounding level; the fused path (one rounding per norm) must not be worse
+    assert e_mine <= 1e-2 and g_mine <= 2e-2, (e_mine, g_mine)
+    assert e_mine <= 2.0 * e_stock + 1e-3 and g_mine <= 2.0 * g_stock + 1e-3, (e_mine, e_stock, g_mine, g_stock)
+
+
+def test_unet_nhwc_graph_capture():
+    """The fused ops are capturable (no syncs, current-stream launches): graphed callable == eager, forward and backward."""
+    from clip_diffusion_b200.unet import create_unet, graph_unet
+
+    m = create_unet(32, seed=2, device="cuda", use_fp16=True)
+    x = torch.randn(1, 3, 64, 64, device="cuda")
+    t = torch.tensor([100.0], device="cuda")
+    xe = x.clone().requires_grad_()
+    ee = m(xe, t)
+    (ge,) = torch.autograd.grad(ee.sum(), xe)
+    gm = graph_unet(m, 64, 64, "cuda")
+    xg = x.clone().requires_grad_()
+    eg = gm(xg, t)
+    (gg,) = torch.autograd.grad(eg.sum(), xg)
+    # same kernels of ours; cuDNN may pick other fp16 algorithms during capture => fp16-rounding-level differences only
+    assert _rel(eg, ee) <= 5e-3 and _rel(gg, ge) <= 5e-3, (_rel(eg, ee), _rel(gg, ge))
