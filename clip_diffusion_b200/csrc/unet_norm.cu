@@ -176,21 +176,47 @@ __device__ __forceinline__ double block_sum_f64(double v, double* red /*>=32*/) 
   return t;
 }
 
+constexpr int kFinalizeThreads = 512;
+
 // one CTA per (sample, group): statistics in fp64 from the chunk partials, then the per-channel affine of the whole
-// normalisation: y = act(a_c * x + b_c),  a_c = rstd*gamma_c*(1+scale_c),  b_c = (beta_c - mean*rstd*gamma_c)*(1+scale_c) + shift_c
-__global__ void __launch_bounds__(128) gn_finalize_fwd_kernel(const float2* __restrict__ partial, int chunks, int C, int G, int HW,
-                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               const float* __restrict__ scale_shift, float eps, float* __restrict__ stats,
-                                                               float* __restrict__ coefA, float* __restrict__ coefB) {
+// normalisation: y = act(a_c * x + b_c),  a_c = rstd*gamma_c*(1+scale_c),  b_c = (beta_c - mean*rstd*gamma_c)*(1+scale_c) + shift_c.
+// pre_bias (the producing convolution's bias, deferred): the normalised tensor is x' = x + pb_c.  Its statistics follow from the
+// per-channel sums of x (sum x' = s + HW*pb, sum x'^2 = q + 2*pb*s + HW*pb^2) and y = a_c*x + (a_c*pb_c + b_c), so the
+// streaming kernels never see it.
+__global__ void __launch_bounds__(kFinalizeThreads) gn_finalize_fwd_kernel(const float2* __restrict__ partial, int chunks, int C, int G, int HW,
+                                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                            const float* __restrict__ scale_shift, const float* __restrict__ pre_bias,
+                                                                            float eps, float* __restrict__ stats, float* __restrict__ coefA,
+                                                                            float* __restrict__ coefB) {
   __shared__ double red[32];
   const int n = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
+  const int total = chunks * cg;
+  const float2* base = partial + (size_t)n * chunks * C + g * cg;
   double s = 0.0, q = 0.0;
-  for (int idx = threadIdx.x; idx < chunks * cg; idx += blockDim.x) {
-    const int p = idx / cg, cc = idx - p * cg;
-    const float2 v = partial[((size_t)n * chunks + p) * C + g * cg + cc];
-    s += (double)v.x;
-    q += (double)v.y;
+  // the loads of one batch are independent: issue four before touching the fp64 accumulators (latency-bound otherwise)
+  for (int idx0 = threadIdx.x; idx0 < total; idx0 += 4 * kFinalizeThreads) {
+    float2 v[4];
+    int cc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = idx0 + k * kFinalizeThreads;
+      const int p = idx / cg;
+      cc[k] = idx - p * cg;
+      v[k] = idx < total ? __ldg(base + (size_t)p * C + cc[k]) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s += (double)v[k].x;
+      q += (double)v[k].y;
+      if (pre_bias && idx0 + k * kFinalizeThreads < total) q += 2.0 * (double)pre_bias[g * cg + cc[k]] * (double)v[k].x;
+    }
   }
+  if (pre_bias)
+    for (int cc = threadIdx.x; cc < cg; cc += blockDim.x) {
+      const double pb = (double)pre_bias[g * cg + cc];
+      s += (double)HW * pb;
+      q += (double)HW * pb * pb;
+    }
   s = block_sum_f64(s, red);
   q = block_sum_f64(q, red);
   const double m = (double)HW * (double)cg;
@@ -214,6 +240,7 @@ __global__ void __launch_bounds__(128) gn_finalize_fwd_kernel(const float2* __re
       a *= sc;
       b = fmaf(b, sc, sh);
     }
+    if (pre_bias) b = fmaf(a, pre_bias[c], b);
     coefA[(size_t)n * C + c] = a;
     coefB[(size_t)n * C + c] = b;
   }
@@ -299,22 +326,39 @@ __global__ void __launch_bounds__(kMaxThreads) gn_bwd_partial_kernel(const TDy* 
   reduce_rows_and_store(s1, s2, C, cvecs, rows_per_iter, red, partial + ((size_t)n * gridDim.x + p) * C);
 }
 
-// with w_c = a_c / rstd (= gamma_c*(1+scale_c)), x^ = (x-mean)*rstd and dx^ = w_c*dv:
-//   dx = rstd*(dx^ - mean_g(dx^) - x^ * mean_g(dx^ x^)) = a_c*dv + B_g*x + C_g
-__global__ void __launch_bounds__(128) gn_finalize_bwd_kernel(const float2* __restrict__ partial, int chunks, int C, int G, int HW,
-                                                               const float* __restrict__ stats, const float* __restrict__ coefA,
-                                                               float* __restrict__ coefBx, float* __restrict__ coefCx) {
+// with w_c = a_c / rstd (= gamma_c*(1+scale_c)), x' = x + pb_c, x^ = (x'-mean)*rstd and dx^ = w_c*dv:
+//   dx = rstd*(dx^ - mean_g(dx^) - x^ * mean_g(dx^ x^)) = a_c*dv + B_g*x' + C_g = a_c*dv + B_g*x + (C_g + B_g*pb_c)
+// (the partial sums are over the raw x: sum dv*x' = S2 + pb_c*S1)
+__global__ void __launch_bounds__(kFinalizeThreads) gn_finalize_bwd_kernel(const float2* __restrict__ partial, int chunks, int C, int G, int HW,
+                                                                            const float* __restrict__ stats, const float* __restrict__ coefA,
+                                                                            const float* __restrict__ pre_bias, float* __restrict__ coefBx,
+                                                                            float* __restrict__ coefCx) {
   __shared__ double red[32];
   const int n = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
   const float mean = stats[2 * blockIdx.x], rstd = stats[2 * blockIdx.x + 1];
+  const int total = chunks * cg;
+  const float2* base = partial + (size_t)n * chunks * C + g * cg;
+  const float* wa = coefA + (size_t)n * C + g * cg;
+  const double inv_rstd = 1.0 / (double)rstd;
   double t1 = 0.0, t2 = 0.0;
-  for (int idx = threadIdx.x; idx < chunks * cg; idx += blockDim.x) {
-    const int p = idx / cg, cc = idx - p * cg;
-    const int c = g * cg + cc;
-    const float2 v = partial[((size_t)n * chunks + p) * C + c];
-    const double w = (double)coefA[(size_t)n * C + c] / (double)rstd;
-    t1 += w * (double)v.x;
-    t2 += w * (double)v.y;
+  for (int idx0 = threadIdx.x; idx0 < total; idx0 += 4 * kFinalizeThreads) {
+    float2 v[4];
+    float w[4], pb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = idx0 + k * kFinalizeThreads;
+      const int p = idx / cg, cc = idx - p * cg;
+      const bool ok = idx < total;
+      v[k] = ok ? __ldg(base + (size_t)p * C + cc) : make_float2(0.f, 0.f);
+      w[k] = ok ? __ldg(wa + cc) : 0.f;
+      pb[k] = (ok && pre_bias) ? __ldg(pre_bias + g * cg + cc) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double wk = (double)w[k] * inv_rstd;
+      t1 += wk * (double)v[k].x;
+      t2 += wk * ((double)v[k].y + (double)pb[k] * (double)v[k].x);
+    }
   }
   t1 = block_sum_f64(t1, red);
   t2 = block_sum_f64(t2, red);
@@ -324,8 +368,9 @@ __global__ void __launch_bounds__(128) gn_finalize_bwd_kernel(const float2* __re
   const double Bg = -(double)rstd * (double)rstd * c2;
   const double Cg = -(double)rstd * c1 - Bg * (double)mean;
   for (int cc = threadIdx.x; cc < cg; cc += blockDim.x) {
-    coefBx[(size_t)n * C + g * cg + cc] = (float)Bg;
-    coefCx[(size_t)n * C + g * cg + cc] = (float)Cg;
+    const int c = g * cg + cc;
+    coefBx[(size_t)n * C + c] = (float)Bg;
+    coefCx[(size_t)n * C + c] = (float)(Cg + (pre_bias ? Bg * (double)pre_bias[c] : 0.0));
   }
 }
 
@@ -367,6 +412,54 @@ __global__ void __launch_bounds__(kMaxThreads) gn_apply_bwd_kernel(const TDy* __
   }
 }
 
+// ---- the other element-wise passes between the convolutions ----------------------------------------------------------------------
+
+// out = a + b + bias_c : the ResBlock's `skip(x) + out_conv(h)` with both convolutions' biases deferred into this one pass
+__global__ void __launch_bounds__(256) bias_residual_add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const float* __restrict__ bias,
+                                                                 long long nvec, int cvecs, __half* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8], bb[8];
+    Row8<__half>::load(a + i * 8, x);
+    Row8<__half>::load(b + i * 8, y);
+    load_coef8(bias + (size_t)(i % cvecs) * 8, bb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = x[j] + y[j] + bb[j];
+    Row8<__half>::store(out + i * 8, x);
+  }
+}
+
+// 2x2 average pooling (UP == false: y[i,j] = scale * sum of the 4 inputs) / nearest 2x upsampling (UP == true: y[i,j] = scale * x[i/2,j/2]).
+// The pair is closed under differentiation: d(avg_pool) = up(scale 0.25), d(upsample) = down(scale 1).  fp32 accumulation like ATen.
+template <bool UP>
+__global__ void __launch_bounds__(256) resample2x_kernel(const __half* __restrict__ x, int Ho, int Wo, int cvecs, long long nvec, float scale,
+                                                          __half* __restrict__ y) {
+  const int Wi = UP ? Wo / 2 : Wo * 2, Hi = UP ? Ho / 2 : Ho * 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvecs);
+    long long pix = i / cvecs;
+    const int xo = (int)(pix % Wo);
+    pix /= Wo;
+    const int yo = (int)(pix % Ho);
+    const long long n = pix / Ho;
+    float acc[8];
+    if (UP) {
+      Row8<__half>::load(x + (((n * Hi + yo / 2) * Wi + xo / 2) * cvecs + cv) * 8, acc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= scale;
+    } else {
+      const __half* p = x + (((n * Hi + 2 * yo) * Wi + 2 * xo) * cvecs + cv) * 8;
+      float v[4][8];
+      Row8<__half>::load(p, v[0]);
+      Row8<__half>::load(p + (size_t)cvecs * 8, v[1]);
+      Row8<__half>::load(p + (size_t)Wi * cvecs * 8, v[2]);
+      Row8<__half>::load(p + (size_t)(Wi + 1) * cvecs * 8, v[3]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = ((v[0][j] + v[1][j]) + (v[2][j] + v[3][j])) * scale;
+    }
+    Row8<__half>::store(y + i * 8, acc);
+  }
+}
+
 int check_shape(int N, int HW, int C, int G) {
   CG_REQUIRE(N >= 1 && HW >= 1 && C >= 8 && G >= 1, "groupnorm_nhwc: bad sizes N=%d HW=%d C=%d G=%d", N, HW, C, G);
   CG_REQUIRE(C % 8 == 0 && C <= 2048, "groupnorm_nhwc: C=%d must be a multiple of 8 and <= 2048", C);
@@ -385,7 +478,8 @@ extern "C" size_t cg_groupnorm_nhwc_workspace_bytes(int N, int HW, int C) {
 }
 
 extern "C" int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G, const float* gamma, const float* beta, const float* scale_shift,
-                                     float eps, int silu, int out_f32, void* y, float* stats, float* coef, void* workspace, void* stream) {
+                                     const float* pre_bias, float eps, int silu, int out_f32, void* y, float* stats, float* coef, void* workspace,
+                                     void* stream) {
   if (int rc = check_shape(N, HW, C, G)) return rc;
   CG_REQUIRE(x && y && gamma && beta && stats && coef && workspace, "groupnorm_nhwc_fwd: null pointer");
   CG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)coef & 15) == 0, "groupnorm_nhwc_fwd: buffers must be 16-byte aligned");
@@ -398,7 +492,7 @@ extern "C" int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G,
   const __half* xh = (const __half*)x;
   gn_stats_partial_kernel<<<grid, g.threads, 0, st>>>(xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, partial);
   CG_LAUNCH_CHECK();
-  gn_finalize_fwd_kernel<<<N * G, 128, 0, st>>>(partial, g.chunks, C, G, HW, gamma, beta, scale_shift, eps, stats, coefA, coefB);
+  gn_finalize_fwd_kernel<<<N * G, kFinalizeThreads, 0, st>>>(partial, g.chunks, C, G, HW, gamma, beta, scale_shift, pre_bias, eps, stats, coefA, coefB);
   CG_LAUNCH_CHECK();
 #define CG_GN_APPLY(S, T) \
   gn_apply_fwd_kernel<S, T><<<grid, g.threads, 0, st>>>(xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB, (T*)y)
@@ -415,7 +509,7 @@ extern "C" int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G,
 }
 
 extern "C" int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, int N, int HW, int C, int G, const float* stats, const float* coef,
-                                     int silu, void* dx, void* workspace, void* stream) {
+                                     const float* pre_bias, int silu, void* dx, void* workspace, void* stream) {
   if (int rc = check_shape(N, HW, C, G)) return rc;
   CG_REQUIRE(dy && x && stats && coef && dx && workspace, "groupnorm_nhwc_bwd: null pointer");
   CG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
@@ -433,7 +527,7 @@ extern "C" int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, 
   do {                                                                                                                                         \
     gn_bwd_partial_kernel<S, T><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB, partial); \
     CG_LAUNCH_CHECK();                                                                                                                         \
-    gn_finalize_bwd_kernel<<<N * G, 128, 0, st>>>(partial, g.chunks, C, G, HW, stats, coefA, coefBx, coefCx);                                  \
+    gn_finalize_bwd_kernel<<<N * G, kFinalizeThreads, 0, st>>>(partial, g.chunks, C, G, HW, stats, coefA, pre_bias, coefBx, coefCx);           \
     CG_LAUNCH_CHECK();                                                                                                                         \
     gn_apply_bwd_kernel<S, T><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB, coefBx, \
                                                           coefCx, (__half*)dx);                                                                \
@@ -447,5 +541,33 @@ extern "C" int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, 
     else CG_GN_BWD(false, __half);
   }
 #undef CG_GN_BWD
+  return 0;
+}
+
+extern "C" int cg_bias_residual_add_nhwc(const void* a, const void* b, const float* bias, int64_t rows, int C, void* out, void* stream) {
+  CG_REQUIRE(a && b && bias && out, "bias_residual_add_nhwc: null pointer");
+  CG_REQUIRE(rows >= 1 && C >= 8 && C % 8 == 0, "bias_residual_add_nhwc: rows=%lld C=%d (C must be a multiple of 8)", (long long)rows, C);
+  CG_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)bias & 15) == 0,
+             "bias_residual_add_nhwc: buffers must be 16-byte aligned");
+  const long long nvec = (long long)rows * (C / 8);
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 16 * CG_NUM_SMS) blocks = 16 * CG_NUM_SMS;
+  bias_residual_add_kernel<<<(int)blocks, 256, 0, cg_stream(stream)>>>((const __half*)a, (const __half*)b, bias, nvec, C / 8, (__half*)out);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cg_resample2x_nhwc(const void* x, int N, int H, int W, int C, int up, float scale, void* y, void* stream) {
+  CG_REQUIRE(x && y, "resample2x_nhwc: null pointer");
+  CG_REQUIRE(N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "resample2x_nhwc: bad sizes N=%d H=%d W=%d C=%d (C must be a multiple of 8)", N, H, W, C);
+  CG_REQUIRE(up || (H % 2 == 0 && W % 2 == 0), "resample2x_nhwc: 2x2 average pooling needs even H, W (got %d x %d)", H, W);
+  CG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "resample2x_nhwc: buffers must be 16-byte aligned");
+  const int Ho = up ? 2 * H : H / 2, Wo = up ? 2 * W : W / 2;
+  const long long nvec = (long long)N * Ho * Wo * (C / 8);
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 16 * CG_NUM_SMS) blocks = 16 * CG_NUM_SMS;
+  if (up) resample2x_kernel<true><<<(int)blocks, 256, 0, cg_stream(stream)>>>((const __half*)x, Ho, Wo, C / 8, nvec, scale, (__half*)y);
+  else resample2x_kernel<false><<<(int)blocks, 256, 0, cg_stream(stream)>>>((const __half*)x, Ho, Wo, C / 8, nvec, scale, (__half*)y);
+  CG_LAUNCH_CHECK();
   return 0;
 }

@@ -33,8 +33,8 @@ def _like_layout(x, t):
 
 class _GroupNormNHWC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, silu, out_f32):
-        _lib.require_cuda(x, gamma, beta, scale_shift)
+    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, silu, out_f32, pre_bias):
+        _lib.require_cuda(x, gamma, beta, scale_shift, pre_bias)
         if x.dtype != torch.float16:
             raise _lib.ClipGuideError("group_norm_nhwc: fp16 activations expected, got %s" % x.dtype)
         N, HW, C = _nhwc_dims(x)
@@ -44,19 +44,23 @@ class _GroupNormNHWC(torch.autograd.Function):
             scale_shift = scale_shift.detach().float().contiguous()
             if tuple(scale_shift.shape) != (N, 2 * C):
                 raise ValueError("scale_shift must be [N, 2C] = %s, got %s" % ((N, 2 * C), tuple(scale_shift.shape)))
+        if pre_bias is not None:
+            pre_bias = pre_bias.detach().float().contiguous()
+            if pre_bias.numel() != C:
+                raise ValueError("pre_bias must have C = %d elements" % C)
         y = torch.empty_like(x, dtype=torch.float32 if out_f32 else torch.float16)  # preserve_format: same NHWC strides
         stats = torch.empty(N, groups, 2, device=x.device, dtype=torch.float32)
         coef = torch.empty(2, N, C, device=x.device, dtype=torch.float32)
         ws = torch.empty(_lib.load().cg_groupnorm_nhwc_workspace_bytes(N, HW, C), device=x.device, dtype=torch.uint8)
         _lib.call("cg_groupnorm_nhwc_fwd", _lib.ptr(x), N, HW, C, int(groups), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(scale_shift),
-                  float(eps), int(bool(silu)), int(bool(out_f32)), _lib.ptr(y), _lib.ptr(stats), _lib.ptr(coef), _lib.ptr(ws))
-        ctx.save_for_backward(x, stats, coef)
+                  _lib.ptr(pre_bias), float(eps), int(bool(silu)), int(bool(out_f32)), _lib.ptr(y), _lib.ptr(stats), _lib.ptr(coef), _lib.ptr(ws))
+        ctx.save_for_backward(x, stats, coef, pre_bias)
         ctx.cfg = (N, HW, C, int(groups), int(bool(silu)), bool(out_f32))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, stats, coef = ctx.saved_tensors
+        x, stats, coef, pre_bias = ctx.saved_tensors
         N, HW, C, groups, silu, out_f32 = ctx.cfg
         dy = _like_layout(x, dy)
         if dy.dtype not in (torch.float16, torch.float32):
@@ -64,14 +68,75 @@ class _GroupNormNHWC(torch.autograd.Function):
         dx = torch.empty_like(x)
         ws = torch.empty(_lib.load().cg_groupnorm_nhwc_workspace_bytes(N, HW, C), device=x.device, dtype=torch.uint8)
         _lib.call("cg_groupnorm_nhwc_bwd", _lib.ptr(dy), int(dy.dtype == torch.float32), _lib.ptr(x), N, HW, C, groups, _lib.ptr(stats),
-                  _lib.ptr(coef), silu, _lib.ptr(dx), _lib.ptr(ws))
-        return dx, None, None, None, None, None, None, None
+                  _lib.ptr(coef), _lib.ptr(pre_bias), silu, _lib.ptr(dx), _lib.ptr(ws))
+        return dx, None, None, None, None, None, None, None, None
 
 
-def group_norm_nhwc(x, gamma, beta, groups=32, eps=1e-5, scale_shift=None, silu=False, out_dtype=None):
-    """act(GroupNorm32(x) * (1 + scale) + shift) for x [N,C,H,W] channels_last (or [N,T,C]) fp16 on CUDA.
+def group_norm_nhwc(x, gamma, beta, groups=32, eps=1e-5, scale_shift=None, silu=False, out_dtype=None, pre_bias=None):
+    """act(GroupNorm32(x + pre_bias) * (1 + scale) + shift) for x [N,C,H,W] channels_last (or [N,T,C]) fp16 on CUDA.
 
     scale_shift: [N, 2C] (the ResBlock's embedding projection, scale | shift) or None; silu: apply SiLU;
-    out_dtype: torch.float16 (default) or torch.float32 (the UNet's fp32 output head)."""
+    out_dtype: torch.float16 (default) or torch.float32 (the UNet's fp32 output head);
+    pre_bias: [C] bias of the convolution that produced x, deferred into this op (no extra memory pass)."""
     out_f32 = out_dtype == torch.float32
-    return _GroupNormNHWC.apply(x, gamma, beta, scale_shift, groups, eps, silu, out_f32)
+    return _GroupNormNHWC.apply(x, gamma, beta, scale_shift, groups, eps, silu, out_f32, pre_bias)
+
+
+def _require_nhwc_half(x, what):
+    if not (x.is_cuda and x.dtype == torch.float16 and x.dim() == 4):
+        raise _lib.ClipGuideError("%s: [N,C,H,W] fp16 CUDA tensor expected (no CPU fallback); got %s %s on %s" % (what, tuple(x.shape), x.dtype, x.device))
+    return x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+
+
+class _BiasResidualAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, bias):
+        a, b = _require_nhwc_half(a, "bias_residual_add"), _require_nhwc_half(b, "bias_residual_add")
+        if a.shape != b.shape:
+            raise ValueError("shape mismatch: %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+        N, C, H, W = a.shape
+        bias = bias.detach().float().contiguous()
+        if bias.numel() != C:
+            raise ValueError("bias must have C = %d elements" % C)
+        out = torch.empty_like(a)
+        _lib.call("cg_bias_residual_add_nhwc", _lib.ptr(a), _lib.ptr(b), _lib.ptr(bias), N * H * W, C, _lib.ptr(out))
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy, None
+
+
+def bias_residual_add(a, b, bias):
+    """a + b + bias[None, :, None, None] in one pass (ResBlock tail `skip(x) + out_conv(h)` with the conv biases deferred)."""
+    return _BiasResidualAdd.apply(a, b, bias)
+
+
+def _resample2x(x, up, scale):
+    x = _require_nhwc_half(x, "resample2x")
+    N, C, H, W = x.shape
+    y = torch.empty((N, C, 2 * H, 2 * W) if up else (N, C, H // 2, W // 2), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    _lib.call("cg_resample2x_nhwc", _lib.ptr(x), N, H, W, C, int(up), float(scale), _lib.ptr(y))
+    return y
+
+
+class _Resample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, up):
+        ctx.up = up
+        return _resample2x(x, up, 1.0 if up else 0.25)
+
+    @staticmethod
+    def backward(ctx, dy):
+        # d(nearest upsample) = sum over each 2x2 window; d(avg_pool 2x2) = 0.25 * nearest upsample
+        return (_resample2x(dy, False, 1.0) if ctx.up else _resample2x(dy, True, 0.25)), None
+
+
+def upsample_nearest2x(x):
+    """F.interpolate(x, scale_factor=2, mode="nearest") on channels_last fp16 (guided-diffusion Upsample without conv)."""
+    return _Resample2x.apply(x, True)
+
+
+def avg_pool2x(x):
+    """F.avg_pool2d(x, 2) on channels_last fp16 (guided-diffusion Downsample without conv)."""
+    return _Resample2x.apply(x, False)

@@ -191,14 +191,24 @@ int cg_dynamic_threshold(const float* x, int B, int64_t n, float q, float min_th
  * x [N,HW,C] fp16 (channels_last), C % 8 == 0, C <= 2048, C % G == 0; gamma, beta [C] fp32; scale_shift [N,2C] fp32 (scale | shift)
  * or NULL; act = SiLU if silu != 0; y [N,HW,C] fp16 (out_f32 == 0) or fp32.  Statistics in fp32/fp64 like GroupNorm32's x.float().
  * stats [N,G,2] (mean, rstd) and coef [2,N,C] (the folded per-channel affine a_c, b_c) are outputs kept for the backward.
+ * pre_bias [C] fp32 or NULL: bias of the convolution that produced x, deferred into this op -- the normalised tensor is x + pre_bias_c
+ * (folded into the per-group statistics and the per-channel affine; costs no memory pass).
  * workspace: cg_groupnorm_nhwc_workspace_bytes(N,HW,C) bytes, 16-byte aligned. */
 size_t cg_groupnorm_nhwc_workspace_bytes(int N, int HW, int C);
 int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G, const float* gamma, const float* beta, const float* scale_shift,
-                          float eps, int silu, int out_f32, void* y, float* stats, float* coef, void* workspace, void* stream);
+                          const float* pre_bias, float eps, int silu, int out_f32, void* y, float* stats, float* coef, void* workspace, void* stream);
 /* input gradient of the above (weights are frozen, models.py:67-71 / :120-127): dy [N,HW,C] fp16 (dy_f32 == 0) or fp32,
  * x / stats / coef as given to / produced by the forward -> dx [N,HW,C] fp16. */
 int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, int N, int HW, int C, int G, const float* stats, const float* coef,
-                          int silu, void* dx, void* workspace, void* stream);
+                          const float* pre_bias, int silu, void* dx, void* workspace, void* stream);
+/* ResBlock tail `skip(x) + out_conv(h)` with the convolution biases deferred: out[r,c] = a[r,c] + b[r,c] + bias[c].
+ * a, b, out [rows, C] fp16 (NHWC rows = N*H*W), bias [C] fp32, C % 8 == 0.  Its gradient is the identity on a and b. */
+int cg_bias_residual_add_nhwc(const void* a, const void* b, const float* bias, int64_t rows, int C, void* out, void* stream);
+/* The resblock_updown resamplers on NHWC fp16 (guided-diffusion Upsample / Downsample without conv, App. A.3):
+ *   up == 0: y [N,H/2,W/2,C] = scale * (sum of each 2x2 window of x [N,H,W,C])   (avg_pool2d: scale 0.25)
+ *   up != 0: y [N,2H,2W,C]   = scale * x[n, i/2, j/2, c]                         (nearest upsampling: scale 1)
+ * Each is the other's gradient (d avg_pool = up with 0.25, d upsample = down with 1).  fp32 accumulation. */
+int cg_resample2x_nhwc(const void* x, int N, int H, int W, int C, int up, float scale, void* y, void* stream);
 
 #ifdef __cplusplus
 }

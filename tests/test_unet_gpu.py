@@ -70,6 +70,65 @@ def test_group_norm_nhwc_forward_backward(case, silu, with_ss, out_f32):
     assert _rel(dx.float(), dxr) <= TOL_BWD, _rel(dx.float(), dxr)
 
 
+@pytest.mark.parametrize("case", [(1, 128, 32, 32, 32), (2, 384, 9, 13, 32), (1, 32, 16, 16, 32), (1, 1024, 8, 8, 32)])
+def test_group_norm_nhwc_deferred_conv_bias(case):
+    """pre_bias: GN(x + b_c) with the producing convolution's bias folded into the statistics / affine (no memory pass)."""
+    from clip_diffusion_b200.unet_ops import group_norm_nhwc
+
+    N, C, H, W, G = case
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(N, C, H, W, generator=g).half()
+    pb = torch.randn(C, generator=g) * 1.5  # as large as the signal: the cross terms of the folded variance matter
+    gamma, beta = 1 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    ss = 0.3 * torch.randn(N, 2 * C, generator=g)
+    dy = torch.randn(N, C, H, W, generator=g).half()
+    xr = x.float().cuda().requires_grad_()
+    yr = _reference(xr + pb.cuda().view(1, -1, 1, 1), gamma.cuda(), beta.cuda(), G, 1e-5, ss.cuda(), True)
+    (dxr,) = torch.autograd.grad(yr, xr, dy.float().cuda())
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = group_norm_nhwc(xc, gamma.cuda(), beta.cuda(), G, 1e-5, scale_shift=ss.cuda(), silu=True, pre_bias=pb.cuda())
+    (dx,) = torch.autograd.grad(y, xc, dy.cuda())
+    assert _rel(y.float(), yr) <= TOL_FWD, _rel(y.float(), yr)
+    assert _rel(dx.float(), dxr) <= TOL_BWD, _rel(dx.float(), dxr)
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 64, 64), (2, 32, 6, 10), (1, 1024, 8, 8), (1, 384, 18, 22)])
+def test_bias_residual_add_and_resample2x(shape):
+    """The ResBlock tail add with deferred biases and the resblock_updown resamplers against the stock torch ops (fp16 rounding only)."""
+    from clip_diffusion_b200 import unet_ops
+
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(C + H)
+    a = torch.randn(shape, generator=g).half().cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    b = torch.randn(shape, generator=g).half().cuda().requires_grad_()  # NCHW on purpose: the op re-lays it out
+    bias = torch.randn(C, generator=g).cuda()
+    out = unet_ops.bias_residual_add(a, b, bias)
+    want = a.float() + b.float() + bias.view(1, -1, 1, 1)
+    assert out.is_contiguous(memory_format=torch.channels_last) and _rel(out.float(), want) <= 5e-4
+    dy = torch.randn(shape, generator=g).half().cuda()
+    ga, gb = torch.autograd.grad(out, (a, b), dy)
+    assert torch.equal(ga, dy) and torch.equal(gb, dy)
+
+    for mine, stock in ((unet_ops.avg_pool2x, lambda t: F.avg_pool2d(t, 2)), (unet_ops.upsample_nearest2x, lambda t: F.interpolate(t, scale_factor=2, mode="nearest"))):
+        x = torch.randn(shape, generator=g).half().cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+        y = mine(x)
+        xr = x.detach().float().requires_grad_()
+        yr = stock(xr)
+        assert y.shape == yr.shape and y.is_contiguous(memory_format=torch.channels_last)
+        assert _rel(y.float(), yr) <= 5e-4
+        dyy = torch.randn(yr.shape, generator=g).half().cuda()
+        (gx,) = torch.autograd.grad(y, x, dyy)
+        (gr,) = torch.autograd.grad(yr, xr, dyy.float())
+        assert _rel(gx.float(), gr) <= 5e-4
+
+
+def test_resample2x_rejects_odd_sizes():
+    from clip_diffusion_b200 import _lib, unet_ops
+
+    with pytest.raises(_lib.ClipGuideError):
+        unet_ops.avg_pool2x(torch.zeros(1, 16, 5, 4, device="cuda").half().contiguous(memory_format=torch.channels_last))
+
+
 def test_group_norm_nhwc_tokens_and_determinism():
     """[N,T,C] token layout (AttentionBlock) and run-to-run bit-identical results (fixed-order reductions, no atomics)."""
     from clip_diffusion_b200.unet_ops import group_norm_nhwc
