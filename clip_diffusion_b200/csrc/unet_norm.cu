@@ -74,18 +74,41 @@ __device__ __forceinline__ float sigmoid_fast(float v) {
   return fmaf(0.5f, t, 0.5f);
 }
 
+// 16-byte read-only load as a volatile asm: the compiler may neither sink it to its first use nor reorder it against its
+// siblings, so the kUnroll loads a thread issues per iteration are really in flight together.  (Written as plain __ldg the
+// loads were re-serialised -- load, convert, accumulate, next address, load ... -- and the reduction kernels ran at 2.7 TB/s.)
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+template <typename T>
+struct Raw8;  // the registers of 8 consecutive channels of one pixel, before conversion
+template <>
+struct Raw8<__half> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __half* p) { u = ldg_stream(p); }
+  __device__ __forceinline__ void get(float* f) const { unpack8(u, f); }
+};
+template <>
+struct Raw8<float> {
+  uint4 u0, u1;
+  __device__ __forceinline__ void load(const float* p) {
+    u0 = ldg_stream(p);
+    u1 = ldg_stream(p + 4);
+  }
+  __device__ __forceinline__ void get(float* f) const {
+    f[0] = __uint_as_float(u0.x); f[1] = __uint_as_float(u0.y); f[2] = __uint_as_float(u0.z); f[3] = __uint_as_float(u0.w);
+    f[4] = __uint_as_float(u1.x); f[5] = __uint_as_float(u1.y); f[6] = __uint_as_float(u1.z); f[7] = __uint_as_float(u1.w);
+  }
+};
+
 template <typename T>
 struct Row8;  // 8 consecutive channels of one pixel
 template <>
 struct Row8<__half> {
   static __device__ __forceinline__ void load(const __half* p, float* f) { unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f); }
-  static __device__ __forceinline__ void zero_or_load(const __half* p, bool ok, float* f) {
-    if (ok) load(p, f);
-    else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = 0.f;
-    }
-  }
   static __device__ __forceinline__ void store(__half* p, const float* f) { *reinterpret_cast<uint4*>(p) = pack8(f); }
 };
 template <>
@@ -93,13 +116,6 @@ struct Row8<float> {
   static __device__ __forceinline__ void load(const float* p, float* f) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-  }
-  static __device__ __forceinline__ void zero_or_load(const float* p, bool ok, float* f) {
-    if (ok) load(p, f);
-    else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = 0.f;
-    }
   }
   static __device__ __forceinline__ void store(float* p, const float* f) {
     reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
@@ -145,22 +161,53 @@ __global__ void __launch_bounds__(kMaxThreads) gn_stats_partial_kernel(const __h
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  for (int row = p * rows_per_chunk + r; row < row_end; row += kUnroll * rows_per_iter) {
-    float v[kUnroll][8];
+  // main loop: kUnroll unconditional loads in flight per thread, pointers advance by a constant stride; then a <kUnroll-row tail
+  const size_t rstride = (size_t)rows_per_iter * C;
+  int row = p * rows_per_chunk + r;
+  const __half* ptr = base + (size_t)row * C;
+  auto accumulate = [&](const Raw8<__half>& raw) {
+    float v[8];
+    raw.get(v);
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      const int rr = row + k * rows_per_iter;
-      Row8<__half>::zero_or_load(base + (size_t)rr * C, rr < row_end, v[k]);
+    for (int j = 0; j < 8; ++j) {
+      s[j] += v[j];
+      q[j] = fmaf(v[j], v[j], q[j]);
     }
+  };
+  for (; row + (kUnroll - 1) * rows_per_iter < row_end; row += kUnroll * rows_per_iter, ptr += kUnroll * rstride) {
+    Raw8<__half> raw[kUnroll];
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k)
+    for (int k = 0; k < kUnroll; ++k) raw[k].load(ptr + k * rstride);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += v[k][j];
-        q[j] = fmaf(v[k][j], v[k][j], q[j]);
-      }
+    for (int k = 0; k < kUnroll; ++k) accumulate(raw[k]);
+  }
+  for (; row < row_end; row += rows_per_iter, ptr += rstride) {
+    Raw8<__half> raw;
+    raw.load(ptr);
+    accumulate(raw);
   }
   reduce_rows_and_store(s, q, C, cvecs, rows_per_iter, red, partial + ((size_t)n * gridDim.x + p) * C);
+}
+
+// both sums of a finalize kernel in ONE pass (two barriers instead of four)
+__device__ __forceinline__ void block_sum2_f64(double& a, double& b, double* red /*>=64*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    red[2 * wid] = a;
+    red[2 * wid + 1] = b;
+  }
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  a = b = 0.0;
+  for (int k = 0; k < nw; ++k) {
+    a += red[2 * k];
+    b += red[2 * k + 1];
+  }
 }
 
 __device__ __forceinline__ double block_sum_f64(double v, double* red /*>=32*/) {
@@ -188,7 +235,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) gn_finalize_fwd_kernel(const
                                                                             const float* __restrict__ scale_shift, const float* __restrict__ pre_bias,
                                                                             float eps, float* __restrict__ stats, float* __restrict__ coefA,
                                                                             float* __restrict__ coefB) {
-  __shared__ double red[32];
+  __shared__ double red[64];
   const int n = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
   const int total = chunks * cg;
   const float2* base = partial + (size_t)n * chunks * C + g * cg;
@@ -217,8 +264,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) gn_finalize_fwd_kernel(const
       s += (double)HW * pb;
       q += (double)HW * pb * pb;
     }
-  s = block_sum_f64(s, red);
-  q = block_sum_f64(q, red);
+  block_sum2_f64(s, q, red);
   const double m = (double)HW * (double)cg;
   const double mean = s / m;
   double var = q / m - mean * mean;
@@ -257,25 +303,31 @@ __global__ void __launch_bounds__(kMaxThreads) gn_apply_fwd_kernel(const __half*
   load_coef8(coefA + (size_t)n * C + col * 8, a);
   load_coef8(coefB + (size_t)n * C + col * 8, b);
   const size_t off = (size_t)n * HW * C + col * 8;
-  for (int row = p * rows_per_chunk + r; row < row_end; row += kUnroll * rows_per_iter) {
-    float v[kUnroll][8];
+  const size_t rstride = (size_t)rows_per_iter * C;
+  int row = p * rows_per_chunk + r;
+  const __half* ptr = x + off + (size_t)row * C;
+  TOut* optr = y + off + (size_t)row * C;
+  auto apply = [&](const Raw8<__half>& raw, TOut* dst) {
+    float v[8];
+    raw.get(v);
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      const int rr = row + k * rows_per_iter;
-      Row8<__half>::zero_or_load(x + off + (size_t)rr * C, rr < row_end, v[k]);
+    for (int j = 0; j < 8; ++j) {
+      const float u = fmaf(a[j], v[j], b[j]);
+      v[j] = SILU ? u * sigmoid_fast(u) : u;
     }
+    Row8<TOut>::store(dst, v);
+  };
+  for (; row + (kUnroll - 1) * rows_per_iter < row_end; row += kUnroll * rows_per_iter, ptr += kUnroll * rstride, optr += kUnroll * rstride) {
+    Raw8<__half> raw[kUnroll];
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      const int rr = row + k * rows_per_iter;
-      if (rr < row_end) {
+    for (int k = 0; k < kUnroll; ++k) raw[k].load(ptr + k * rstride);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float u = fmaf(a[j], v[k][j], b[j]);
-          v[k][j] = SILU ? u * sigmoid_fast(u) : u;
-        }
-        Row8<TOut>::store(y + off + (size_t)rr * C, v[k]);
-      }
-    }
+    for (int k = 0; k < kUnroll; ++k) apply(raw[k], optr + k * rstride);
+  }
+  for (; row < row_end; row += rows_per_iter, ptr += rstride, optr += rstride) {
+    Raw8<__half> raw;
+    raw.load(ptr);
+    apply(raw, optr);
   }
 }
 
@@ -306,22 +358,38 @@ __global__ void __launch_bounds__(kMaxThreads) gn_bwd_partial_kernel(const TDy* 
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   constexpr int U = 2;  // two (dy, x) row pairs in flight: same bytes in flight as the forward's four
-  for (int row = p * rows_per_chunk + r; row < row_end; row += U * rows_per_iter) {
-    float xv[U][8], gv[U][8];
+  const size_t rstride = (size_t)rows_per_iter * C;
+  int row = p * rows_per_chunk + r;
+  const __half* xp = x + off + (size_t)row * C;
+  const TDy* gp = dy + off + (size_t)row * C;
+  auto accumulate = [&](const Raw8<__half>& xr, const Raw8<TDy>& gr) {
+    float xv[8], gv[8];
+    xr.get(xv);
+    gr.get(gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dv = dact<SILU>(gv[j], SILU ? fmaf(a[j], xv[j], b[j]) : 0.f);
+      s1[j] += dv;
+      s2[j] = fmaf(dv, xv[j], s2[j]);
+    }
+  };
+  for (; row + (U - 1) * rows_per_iter < row_end; row += U * rows_per_iter, xp += U * rstride, gp += U * rstride) {
+    Raw8<__half> xr[U];
+    Raw8<TDy> gr[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      const int rr = row + k * rows_per_iter;
-      Row8<__half>::zero_or_load(x + off + (size_t)rr * C, rr < row_end, xv[k]);
-      Row8<TDy>::zero_or_load(dy + off + (size_t)rr * C, rr < row_end, gv[k]);
+      xr[k].load(xp + k * rstride);
+      gr[k].load(gp + k * rstride);
     }
 #pragma unroll
-    for (int k = 0; k < U; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dv = dact<SILU>(gv[k][j], SILU ? fmaf(a[j], xv[k][j], b[j]) : 0.f);
-        s1[j] += dv;
-        s2[j] = fmaf(dv, xv[k][j], s2[j]);
-      }
+    for (int k = 0; k < U; ++k) accumulate(xr[k], gr[k]);
+  }
+  for (; row < row_end; row += rows_per_iter, xp += rstride, gp += rstride) {
+    Raw8<__half> xr;
+    Raw8<TDy> gr;
+    xr.load(xp);
+    gr.load(gp);
+    accumulate(xr, gr);
   }
   reduce_rows_and_store(s1, s2, C, cvecs, rows_per_iter, red, partial + ((size_t)n * gridDim.x + p) * C);
 }
@@ -333,7 +401,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) gn_finalize_bwd_kernel(const
                                                                             const float* __restrict__ stats, const float* __restrict__ coefA,
                                                                             const float* __restrict__ pre_bias, float* __restrict__ coefBx,
                                                                             float* __restrict__ coefCx) {
-  __shared__ double red[32];
+  __shared__ double red[64];
   const int n = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
   const float mean = stats[2 * blockIdx.x], rstd = stats[2 * blockIdx.x + 1];
   const int total = chunks * cg;
@@ -360,8 +428,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) gn_finalize_bwd_kernel(const
       t2 += wk * ((double)v[k].y + (double)pb[k] * (double)v[k].x);
     }
   }
-  t1 = block_sum_f64(t1, red);
-  t2 = block_sum_f64(t2, red);
+  block_sum2_f64(t1, t2, red);
   const double m = (double)HW * (double)cg;
   const double c1 = t1 / m;
   const double c2 = (double)rstd * (t2 - (double)mean * t1) / m;
@@ -389,26 +456,39 @@ __global__ void __launch_bounds__(kMaxThreads) gn_apply_bwd_kernel(const TDy* __
   load_coef8(coefCx + (size_t)n * C + col * 8, cx);
   const size_t off = (size_t)n * HW * C + col * 8;
   constexpr int U = 2;
-  for (int row = p * rows_per_chunk + r; row < row_end; row += U * rows_per_iter) {
-    float xv[U][8], gv[U][8];
+  const size_t rstride = (size_t)rows_per_iter * C;
+  int row = p * rows_per_chunk + r;
+  const __half* xp = x + off + (size_t)row * C;
+  const TDy* gp = dy + off + (size_t)row * C;
+  __half* op = dx + off + (size_t)row * C;
+  auto apply = [&](const Raw8<__half>& xr, const Raw8<TDy>& gr, __half* dst) {
+    float xv[8], gv[8];
+    xr.get(xv);
+    gr.get(gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dv = dact<SILU>(gv[j], SILU ? fmaf(a[j], xv[j], b[j]) : 0.f);
+      gv[j] = fmaf(a[j], dv, fmaf(bx[j], xv[j], cx[j]));
+    }
+    Row8<__half>::store(dst, gv);
+  };
+  for (; row + (U - 1) * rows_per_iter < row_end; row += U * rows_per_iter, xp += U * rstride, gp += U * rstride, op += U * rstride) {
+    Raw8<__half> xr[U];
+    Raw8<TDy> gr[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      const int rr = row + k * rows_per_iter;
-      Row8<__half>::zero_or_load(x + off + (size_t)rr * C, rr < row_end, xv[k]);
-      Row8<TDy>::zero_or_load(dy + off + (size_t)rr * C, rr < row_end, gv[k]);
+      xr[k].load(xp + k * rstride);
+      gr[k].load(gp + k * rstride);
     }
 #pragma unroll
-    for (int k = 0; k < U; ++k) {
-      const int rr = row + k * rows_per_iter;
-      if (rr < row_end) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float dv = dact<SILU>(gv[k][j], SILU ? fmaf(a[j], xv[k][j], b[j]) : 0.f);
-          gv[k][j] = fmaf(a[j], dv, fmaf(bx[j], xv[k][j], cx[j]));
-        }
-        Row8<__half>::store(dx + off + (size_t)rr * C, gv[k]);
-      }
-    }
+    for (int k = 0; k < U; ++k) apply(xr[k], gr[k], op + k * rstride);
+  }
+  for (; row < row_end; row += rows_per_iter, xp += rstride, gp += rstride, op += rstride) {
+    Raw8<__half> xr;
+    Raw8<TDy> gr;
+    xr.load(xp);
+    gr.load(gp);
+    apply(xr, gr, op);
   }
 }
 
@@ -457,6 +537,22 @@ __global__ void __launch_bounds__(256) resample2x_kernel(const __half* __restric
       for (int j = 0; j < 8; ++j) acc[j] = ((v[0][j] + v[1][j]) + (v[2][j] + v[3][j])) * scale;
     }
     Row8<__half>::store(y + i * 8, acc);
+  }
+}
+
+// torch.cat([a, b], dim=1) on NHWC rows (SPLIT == false: out[r] = a[r] | b[r]) and its gradient (SPLIT == true: the two
+// contiguous halves of one row-interleaved tensor).  Pure 128-bit copies; ATen's generic cat / strided-slice copies ran at
+// ~1/4 of HBM speed on these shapes.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) concat2_kernel(uint4* __restrict__ a, int ca, uint4* __restrict__ b, int cb, long long nvec,
+                                                       uint4* __restrict__ cat) {
+  const int ct = ca + cb;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ct;
+    const int cv = (int)(i - r * ct);
+    uint4* part = cv < ca ? a + r * ca + cv : b + r * cb + (cv - ca);
+    if (SPLIT) *part = __ldg(cat + i);
+    else cat[i] = __ldg(part);
   }
 }
 
@@ -568,6 +664,20 @@ extern "C" int cg_resample2x_nhwc(const void* x, int N, int H, int W, int C, int
   if (blocks > 16 * CG_NUM_SMS) blocks = 16 * CG_NUM_SMS;
   if (up) resample2x_kernel<true><<<(int)blocks, 256, 0, cg_stream(stream)>>>((const __half*)x, Ho, Wo, C / 8, nvec, scale, (__half*)y);
   else resample2x_kernel<false><<<(int)blocks, 256, 0, cg_stream(stream)>>>((const __half*)x, Ho, Wo, C / 8, nvec, scale, (__half*)y);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cg_concat2_nhwc(void* a, int Ca, void* b, int Cb, int64_t rows, void* cat, int split, void* stream) {
+  CG_REQUIRE(a && b && cat, "concat2_nhwc: null pointer");
+  CG_REQUIRE(rows >= 1 && Ca >= 8 && Cb >= 8 && Ca % 8 == 0 && Cb % 8 == 0, "concat2_nhwc: rows=%lld Ca=%d Cb=%d (channel counts must be multiples of 8)",
+             (long long)rows, Ca, Cb);
+  CG_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)cat & 15) == 0, "concat2_nhwc: buffers must be 16-byte aligned");
+  const long long nvec = (long long)rows * ((Ca + Cb) / 8);
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 16 * CG_NUM_SMS) blocks = 16 * CG_NUM_SMS;
+  if (split) concat2_kernel<true><<<(int)blocks, 256, 0, cg_stream(stream)>>>((uint4*)a, Ca / 8, (uint4*)b, Cb / 8, nvec, (uint4*)cat);
+  else concat2_kernel<false><<<(int)blocks, 256, 0, cg_stream(stream)>>>((uint4*)a, Ca / 8, (uint4*)b, Cb / 8, nvec, (uint4*)cat);
   CG_LAUNCH_CHECK();
   return 0;
 }

@@ -296,8 +296,11 @@ class UNetModel(nn.Module):
             h = blk(h, emb)
             hs.append(h)
         h = self.middle_block(h, emb)
+        fused = self.channels_last and h.is_cuda and h.dtype == torch.float16
+        if fused:
+            from clip_diffusion_b200.unet_ops import concat_channels
         for blk in self.output_blocks:
-            h = blk(torch.cat([h, hs.pop()], dim=1), emb)
+            h = blk(concat_channels(h, hs.pop()) if fused else torch.cat([h, hs.pop()], dim=1), emb)
         if self.channels_last and h.is_cuda and h.dtype == torch.float16:
             h = self.out_norm(h, silu=True, out_dtype=x.dtype)  # fp32 statistics and fp32 output from the fp16 trunk, one pass
         else:

@@ -140,3 +140,35 @@ def upsample_nearest2x(x):
 def avg_pool2x(x):
     """F.avg_pool2d(x, 2) on channels_last fp16 (guided-diffusion Downsample without conv)."""
     return _Resample2x.apply(x, False)
+
+
+def _split_channels(cat, ca, cb):
+    cat = _require_nhwc_half(cat, "concat_channels backward")
+    N, C, H, W = cat.shape
+    a = torch.empty((N, ca, H, W), device=cat.device, dtype=cat.dtype, memory_format=torch.channels_last)
+    b = torch.empty((N, cb, H, W), device=cat.device, dtype=cat.dtype, memory_format=torch.channels_last)
+    _lib.call("cg_concat2_nhwc", _lib.ptr(a), ca, _lib.ptr(b), cb, N * H * W, _lib.ptr(cat), 1)
+    return a, b
+
+
+class _ConcatChannels(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _require_nhwc_half(a, "concat_channels"), _require_nhwc_half(b, "concat_channels")
+        if a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+            raise ValueError("shape mismatch: %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+        N, ca, H, W = a.shape
+        cb = b.shape[1]
+        out = torch.empty((N, ca + cb, H, W), device=a.device, dtype=a.dtype, memory_format=torch.channels_last)
+        _lib.call("cg_concat2_nhwc", _lib.ptr(a), ca, _lib.ptr(b), cb, N * H * W, _lib.ptr(out), 0)
+        ctx.widths = (ca, cb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _split_channels(dy, *ctx.widths)  # two dense tensors in one pass (not strided views that every consumer re-copies)
+
+
+def concat_channels(a, b):
+    """torch.cat([a, b], dim=1) on channels_last fp16 (the UNet's skip connections), with a one-pass split as its gradient."""
+    return _ConcatChannels.apply(a, b)

@@ -209,6 +209,11 @@ int cg_bias_residual_add_nhwc(const void* a, const void* b, const float* bias, i
  *   up != 0: y [N,2H,2W,C]   = scale * x[n, i/2, j/2, c]                         (nearest upsampling: scale 1)
  * Each is the other's gradient (d avg_pool = up with 0.25, d upsample = down with 1).  fp32 accumulation. */
 int cg_resample2x_nhwc(const void* x, int N, int H, int W, int C, int up, float scale, void* y, void* stream);
+/* The UNet's skip connections, `torch.cat([h, hs.pop()], dim=1)` on NHWC fp16 rows (guided-diffusion UNetModel.forward):
+ *   split == 0: cat[r, 0:Ca] = a[r, :], cat[r, Ca:Ca+Cb] = b[r, :]     (a, b are read)
+ *   split != 0: the inverse -- a and b are WRITTEN from cat             (the concatenation's gradient)
+ * a [rows,Ca], b [rows,Cb], cat [rows,Ca+Cb] fp16; Ca, Cb multiples of 8. */
+int cg_concat2_nhwc(void* a, int Ca, void* b, int Cb, int64_t rows, void* cat, int split, void* stream);
 
 #ifdef __cplusplus
 }

@@ -122,6 +122,22 @@ def test_bias_residual_add_and_resample2x(shape):
         assert _rel(gx.float(), gr) <= 5e-4
 
 
+@pytest.mark.parametrize("shape,cb", [((1, 128, 32, 32), 128), ((2, 256, 5, 7), 128), ((1, 1024, 8, 8), 512), ((1, 8, 3, 3), 24)])
+def test_concat_channels_and_split_gradient(shape, cb):
+    from clip_diffusion_b200 import unet_ops
+
+    N, ca, H, W = shape
+    g = torch.Generator().manual_seed(ca + cb)
+    a = torch.randn(N, ca, H, W, generator=g).half().cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    b = torch.randn(N, cb, H, W, generator=g).half().cuda().requires_grad_()  # NCHW: re-laid out by the op
+    out = unet_ops.concat_channels(a, b)
+    assert out.is_contiguous(memory_format=torch.channels_last) and torch.equal(out, torch.cat([a, b], dim=1))
+    dy = torch.randn(N, ca + cb, H, W, generator=g).half().cuda()
+    ga, gb = torch.autograd.grad(out, (a, b), dy)
+    assert torch.equal(ga, dy[:, :ca]) and torch.equal(gb, dy[:, ca:])
+    assert ga.is_contiguous(memory_format=torch.channels_last) and gb.is_contiguous(memory_format=torch.channels_last)
+
+
 def test_resample2x_rejects_odd_sizes():
     from clip_diffusion_b200 import _lib, unet_ops
 
