@@ -112,6 +112,37 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
 
 
+def unet_norm_roofline(dev, hbm_peak):
+    """Second roofline object: the HBM-bound op that dominates the replicated UNet's non-conv time (csrc/unet_norm.cu), timed live with
+    CUDA events on the launching stream at the level-0 shape of the 512x512 UNet, L2 flushed (512 MB memset) between iterations.
+    Algorithmic bytes: forward reads x twice and writes y (3 passes), backward reads (dy, x) twice and writes dx (5 passes)."""
+    from clip_diffusion_b200.unet_ops import group_norm_nhwc
+
+    shape = (1, 128, 512, 512)
+    x = torch.randn(shape, device=dev).half().contiguous(memory_format=torch.channels_last).requires_grad_()
+    gamma, beta = torch.ones(shape[1], device=dev), torch.zeros(shape[1], device=dev)
+    ss = torch.zeros(1, 2 * shape[1], device=dev)
+    dy = torch.randn(shape, device=dev).half().contiguous(memory_format=torch.channels_last)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    nb = x.numel() * 2
+    ts = []
+    for it in range(8):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = group_norm_nhwc(x, gamma, beta, 32, 1e-5, scale_shift=ss, silu=True)
+        torch.autograd.grad(y, x, dy)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    achieved = 8 * nb / (ms / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": "cg_groupnorm_nhwc_fwd + _bwd (GroupNorm32+scale-shift+SiLU, 3 + 3 kernels) on [1,512,512,128] fp16 NHWC",
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "algorithmic_bytes": 8 * nb, "ms": ms,
+            "note": "op-level (includes the two tiny finalize kernels and host launch gaps); per-kernel numbers in profiles/r01_unet_kernel_rooflines.txt"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -218,6 +249,7 @@ def main():
     from clip_diffusion_b200.unet import create_unet, graph_unet
     from clip_diffusion_b200.utils.functional import set_seed
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     torch.backends.cudnn.benchmark = os.environ.get("CG_CUDNN_BENCHMARK", "1") == "1"  # let cuDNN pick conv algorithms for the static UNet shapes
@@ -306,6 +338,8 @@ def main():
     wall1 = time.time()
     ms = tmax(e0.elapsed_time(e1))
     launches = _lib.kernel_launches - k0
+    if unet_graphed:  # our GroupNorm / resample / concat kernels replayed inside the UNet's CUDA graphs (one forward + one backward per step)
+        launches += K * unet.own_kernels_per_replay
     prof, vit_ops.PROFILE = vit_ops.PROFILE, None
     gemm_ms = sum(a.elapsed_time(b) for _, a, b in prof)
     gemm_flops = sum(f for f, _, _ in prof)
@@ -352,6 +386,8 @@ def main():
                      "algorithmic_flops_per_launch": gemm_flops / max(len(prof), 1), "peak_source": peak_src, "launches": len(prof),
                      "share_of_step": gemm_ms / ms if ms > 0 else None},
     }
+    if unet is not None and args.unet_layout == "nhwc":
+        line["roofline_unet_norm"] = unet_norm_roofline(dev, hbm_peak)
     if world == 1 and not args.no_cpu_baseline and not clip_only:
         torch.set_num_threads(os.cpu_count() or 1)
         cstep, cx, cddim, ccuts = build_cpu_reference(args.workload)

@@ -335,13 +335,21 @@ def graph_unet(model, height, width=None, device="cuda"):
     (profiles/r01_*): with graphs the step is bounded by device time instead of launch overhead.  Returns a callable with the
     module's signature ``(x, timesteps, y=None)``; ``x`` must require grad (use ``GuidanceStep.ddim_step``, which always
     evaluates the UNet once, with grad)."""
+    from clip_diffusion_b200 import _lib
+
     width = width or height
     sx = torch.randn(1, 3, height, width, device=device, requires_grad=True)
     st = torch.full((1,), 500.0, device=device)
+    # kernels of csrc/unet_norm.cu that one forward + backward launches (eager, counted by the ctypes binding): inside the graphs
+    # they replay without passing through Python, so callers that report launch counts add this per replayed step
+    k0 = _lib.kernel_launches
+    torch.autograd.grad(model(sx, st).float().sum(), sx)
+    own_kernels = _lib.kernel_launches - k0
     graphed = torch.cuda.make_graphed_callables(model, (sx, st))
 
     def call(x, timesteps, y=None):
         return graphed(x, timesteps.to(torch.float32))
 
     call.module = model
+    call.own_kernels_per_replay = own_kernels
     return call
