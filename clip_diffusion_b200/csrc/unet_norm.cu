@@ -445,7 +445,8 @@ template <bool SILU, typename TDy>
 __global__ void __launch_bounds__(kMaxThreads) gn_apply_bwd_kernel(const TDy* __restrict__ dy, const __half* __restrict__ x, int HW, int C, int cvecs,
                                                                     int rows_per_iter, int rows_per_chunk, const float* __restrict__ coefA,
                                                                     const float* __restrict__ coefB, const float* __restrict__ coefBx,
-                                                                    const float* __restrict__ coefCx, __half* __restrict__ dx) {
+                                                                    const float* __restrict__ coefCx, const __half* __restrict__ dres,
+                                                                    __half* __restrict__ dx) {
   const int n = blockIdx.y, p = blockIdx.x;
   const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
   const int row_end = min(HW, (p + 1) * rows_per_chunk);
@@ -461,14 +462,18 @@ __global__ void __launch_bounds__(kMaxThreads) gn_apply_bwd_kernel(const TDy* __
   const __half* xp = x + off + (size_t)row * C;
   const TDy* gp = dy + off + (size_t)row * C;
   __half* op = dx + off + (size_t)row * C;
+  // dres: gradient reaching x through its OTHER consumer (the block's skip path), added here instead of in a separate pass
+  const ptrdiff_t res_off = dres ? (dres - dx) : 0;
   auto apply = [&](const Raw8<__half>& xr, const Raw8<TDy>& gr, __half* dst) {
-    float xv[8], gv[8];
+    float xv[8], gv[8], rv[8];
+    if (dres) Row8<__half>::load(dst + res_off, rv);
     xr.get(xv);
     gr.get(gv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float dv = dact<SILU>(gv[j], SILU ? fmaf(a[j], xv[j], b[j]) : 0.f);
       gv[j] = fmaf(a[j], dv, fmaf(bx[j], xv[j], cx[j]));
+      if (dres) gv[j] += rv[j];
     }
     Row8<__half>::store(dst, gv);
   };
@@ -605,10 +610,11 @@ extern "C" int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G,
 }
 
 extern "C" int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, int N, int HW, int C, int G, const float* stats, const float* coef,
-                                     const float* pre_bias, int silu, void* dx, void* workspace, void* stream) {
+                                     const float* pre_bias, int silu, const void* dres, void* dx, void* workspace, void* stream) {
   if (int rc = check_shape(N, HW, C, G)) return rc;
   CG_REQUIRE(dy && x && stats && coef && dx && workspace, "groupnorm_nhwc_bwd: null pointer");
-  CG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+  CG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)workspace & 15) == 0 &&
+                 ((uintptr_t)dres & 15) == 0,
              "groupnorm_nhwc_bwd: buffers must be 16-byte aligned");
   const Geo g = geometry(N, HW, C);
   cudaStream_t st = cg_stream(stream);
@@ -626,7 +632,7 @@ extern "C" int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, 
     gn_finalize_bwd_kernel<<<N * G, kFinalizeThreads, 0, st>>>(partial, g.chunks, C, G, HW, stats, coefA, pre_bias, coefBx, coefCx);           \
     CG_LAUNCH_CHECK();                                                                                                                         \
     gn_apply_bwd_kernel<S, T><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB, coefBx, \
-                                                          coefCx, (__half*)dx);                                                                \
+                                                          coefCx, (const __half*)dres, (__half*)dx);                                                                \
     CG_LAUNCH_CHECK();                                                                                                                         \
   } while (0)
   if (silu) {

@@ -99,9 +99,19 @@ __global__ void __launch_bounds__(128) proj_fwd_kernel(const float* __restrict__
   __syncthreads();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
-  float acc = 0.f;
-  for (int d = 0; d < D; ++d) acc = fmaf(ys[d], __ldg(proj + (long long)d * E + e), acc);
-  emb[(long long)n * E + e] = acc;
+  // eight independent loads in flight and four accumulators (a single dependent chain of D L2 round trips took 75-110 us)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* pp = proj + e;
+  int d = 0;
+  for (; d + 8 <= D; d += 8) {
+    float w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __ldg(pp + (long long)(d + k) * E);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k & 3] = fmaf(ys[d + k], w[k], acc[k & 3]);
+  }
+  for (; d < D; ++d) acc[0] = fmaf(ys[d], __ldg(pp + (long long)d * E), acc[0]);
+  emb[(long long)n * E + e] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
 // dy[n,d] = sum_e demb[n,e] proj[d,e];  one warp per (n,d)

@@ -93,14 +93,15 @@ class GroupNorm32(nn.GroupNorm):
 
     nhwc = False
 
-    def forward(self, x, scale_shift=None, silu=False, out_dtype=None, pre_bias=None):
+    def forward(self, x, scale_shift=None, silu=False, out_dtype=None, pre_bias=None, passthrough=False):
         if self.nhwc and x.is_cuda and x.dtype == torch.float16:
             from clip_diffusion_b200.unet_ops import group_norm_nhwc
 
             if x.dim() == 4 and not x.is_contiguous(memory_format=torch.channels_last):
                 x = x.contiguous(memory_format=torch.channels_last)
             return group_norm_nhwc(x, self.weight, self.bias, self.num_groups, self.eps, scale_shift=scale_shift, silu=silu, out_dtype=out_dtype,
-                                   pre_bias=pre_bias)
+                                   pre_bias=pre_bias, passthrough=passthrough)
+        assert not passthrough, "passthrough is a feature of the fused NHWC op"
         if pre_bias is not None:
             x = x + pre_bias.type(x.dtype).view(1, -1, *([1] * (x.dim() - 2)))
         if x.is_cuda and x.dtype == torch.float16:
@@ -149,9 +150,13 @@ class ResBlock(nn.Module):
         self.out_conv = nn.Conv2d(out_channels, out_channels, 3, padding=1)
         self.skip = nn.Identity() if out_channels == channels else nn.Conv2d(channels, out_channels, 1)
         self._fused_bias = None
+        self._scale_shift = None  # set per forward by UNetModel._project_embeddings (fused NHWC path)
 
     def forward(self, x, emb):
-        h = self.in_norm(x, silu=True)
+        if self.in_norm.nhwc and x.is_cuda and x.dtype == torch.float16:
+            h, x = self.in_norm(x, silu=True, passthrough=True)  # x: alias for the skip path (gradients summed in the norm's backward kernel)
+        else:
+            h = self.in_norm(x, silu=True)
         if self.resample is not None:
             h = self.resample(h)
             x = self.resample(x)
@@ -176,7 +181,9 @@ class ResBlock(nn.Module):
             self._fused_bias = (self.in_conv.bias.detach().float().contiguous(), tail.contiguous())
         b_in, b_tail = self._fused_bias
         h = F.conv2d(h, self.in_conv.weight, None, padding=1)
-        h = self.out_norm(h, scale_shift=self.emb(F.silu(emb)), silu=True, pre_bias=b_in)
+        # scale-shift of this block: a slice of the model-wide batched projection when UNetModel.forward prepared one
+        ss = self._scale_shift if self._scale_shift is not None else self.emb(F.silu(emb))
+        h = self.out_norm(h, scale_shift=ss, silu=True, pre_bias=b_in)
         h = F.conv2d(h, self.out_conv.weight, None, padding=1)
         skip = x if isinstance(self.skip, nn.Identity) else F.conv2d(x, self.skip.weight, None)
         return bias_residual_add(h, skip, b_tail)
@@ -210,7 +217,8 @@ class AttentionBlock(nn.Module):
             x = x.contiguous(memory_format=torch.channels_last)
         t = hh * ww
         tok = x.permute(0, 2, 3, 1).reshape(b, t, c)  # a view
-        qkv = F.linear(self.norm(tok), self.qkv.weight.squeeze(-1), self.qkv.bias)
+        normed, tok = self.norm(tok, passthrough=True)
+        qkv = F.linear(normed, self.qkv.weight.squeeze(-1), self.qkv.bias)
         q, k, v = qkv.view(b, t, self.heads, 3, c // self.heads).permute(3, 0, 2, 1, 4)
         a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, t, c)
         out = tok + F.linear(a, self.proj.weight.squeeze(-1), self.proj.bias)
@@ -247,6 +255,7 @@ class UNetModel(nn.Module):
         self.model_channels = mc
         self.dtype = torch.float16 if use_fp16 else torch.float32
         self.channels_last = False  # set by create_unet(..., channels_last=True): NHWC activations/weights for cuDNN
+        self._emb_cat = None
         emb_ch = mc * 4
         self.time_embed = nn.Sequential(nn.Linear(mc, emb_ch), nn.SiLU(), nn.Linear(emb_ch, emb_ch))
         ch = in_ch = int(mult[0] * mc)
@@ -286,11 +295,27 @@ class UNetModel(nn.Module):
                     if isinstance(mod, (nn.Conv1d, nn.Conv2d)):  # as guided-diffusion: convs only, Linear stays fp32
                         mod.half()
 
+    def _project_embeddings(self, emb):
+        """All ResBlocks' `emb_layers` (SiLU -> Linear(emb_ch, 2C)) as ONE fp32 GEMV over the concatenated weights instead of 49 SiLU +
+        49 GEMV launches of ~7 us each (the timestep embedding is the same for every block; weights are frozen, so the
+        concatenation is built once)."""
+        if self._emb_cat is None:
+            blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
+            w = torch.cat([b.emb.weight.detach() for b in blocks]).contiguous()
+            bias = torch.cat([b.emb.bias.detach() for b in blocks]).contiguous()
+            self._emb_cat = (blocks, w, bias, [b.emb.out_features for b in blocks])
+        blocks, w, bias, widths = self._emb_cat
+        all_ss = F.linear(F.silu(emb), w, bias)
+        for blk, ss in zip(blocks, all_ss.split(widths, dim=1)):
+            blk._scale_shift = ss
+
     def forward(self, x, timesteps, y=None):
         emb = self.time_embed(timestep_embedding(timesteps, self.model_channels))
         h = x.type(self.dtype)
         if self.channels_last:
             h = h.contiguous(memory_format=torch.channels_last)
+            if h.is_cuda and h.dtype == torch.float16:
+                self._project_embeddings(emb)
         hs = []
         for blk in self.input_blocks:
             h = blk(h, emb)

@@ -33,7 +33,7 @@ def _like_layout(x, t):
 
 class _GroupNormNHWC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, silu, out_f32, pre_bias):
+    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, silu, out_f32, pre_bias, passthrough):
         _lib.require_cuda(x, gamma, beta, scale_shift, pre_bias)
         if x.dtype != torch.float16:
             raise _lib.ClipGuideError("group_norm_nhwc: fp16 activations expected, got %s" % x.dtype)
@@ -56,30 +56,41 @@ class _GroupNormNHWC(torch.autograd.Function):
                   _lib.ptr(pre_bias), float(eps), int(bool(silu)), int(bool(out_f32)), _lib.ptr(y), _lib.ptr(stats), _lib.ptr(coef), _lib.ptr(ws))
         ctx.save_for_backward(x, stats, coef, pre_bias)
         ctx.cfg = (N, HW, C, int(groups), int(bool(silu)), bool(out_f32))
+        ctx.set_materialize_grads(False)  # an unused output's gradient arrives as None, not as a zero tensor
+        if passthrough:
+            # second output = x itself, for the block's residual / skip path: both gradients then arrive in ONE backward call and
+            # are summed inside the apply kernel (autograd would otherwise accumulate them in a separate read-read-write pass)
+            return y, torch.ops.aten.alias(x)  # NOT view_as: that rewrites the stride of size-1 dims and cuDNN then stops seeing NHWC
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dres=None):
         x, stats, coef, pre_bias = ctx.saved_tensors
         N, HW, C, groups, silu, out_f32 = ctx.cfg
+        if dy is None:  # only the pass-through output was used
+            return (dres,) + (None,) * 9
         dy = _like_layout(x, dy)
         if dy.dtype not in (torch.float16, torch.float32):
             dy = dy.float()
+        if dres is not None:
+            dres = _like_layout(x, dres.to(torch.float16))
         dx = torch.empty_like(x)
         ws = torch.empty(_lib.load().cg_groupnorm_nhwc_workspace_bytes(N, HW, C), device=x.device, dtype=torch.uint8)
         _lib.call("cg_groupnorm_nhwc_bwd", _lib.ptr(dy), int(dy.dtype == torch.float32), _lib.ptr(x), N, HW, C, groups, _lib.ptr(stats),
-                  _lib.ptr(coef), _lib.ptr(pre_bias), silu, _lib.ptr(dx), _lib.ptr(ws))
-        return dx, None, None, None, None, None, None, None, None
+                  _lib.ptr(coef), _lib.ptr(pre_bias), silu, _lib.ptr(dres), _lib.ptr(dx), _lib.ptr(ws))
+        return (dx,) + (None,) * 9
 
 
-def group_norm_nhwc(x, gamma, beta, groups=32, eps=1e-5, scale_shift=None, silu=False, out_dtype=None, pre_bias=None):
+def group_norm_nhwc(x, gamma, beta, groups=32, eps=1e-5, scale_shift=None, silu=False, out_dtype=None, pre_bias=None, passthrough=False):
     """act(GroupNorm32(x + pre_bias) * (1 + scale) + shift) for x [N,C,H,W] channels_last (or [N,T,C]) fp16 on CUDA.
 
     scale_shift: [N, 2C] (the ResBlock's embedding projection, scale | shift) or None; silu: apply SiLU;
     out_dtype: torch.float16 (default) or torch.float32 (the UNet's fp32 output head);
-    pre_bias: [C] bias of the convolution that produced x, deferred into this op (no extra memory pass)."""
+    pre_bias: [C] bias of the convolution that produced x, deferred into this op (no extra memory pass);
+    passthrough: return (y, x') with x' an alias of x to be used by the block's residual / skip path -- the two gradients of x are
+    then summed inside the backward kernel."""
     out_f32 = out_dtype == torch.float32
-    return _GroupNormNHWC.apply(x, gamma, beta, scale_shift, groups, eps, silu, out_f32, pre_bias)
+    return _GroupNormNHWC.apply(x, gamma, beta, scale_shift, groups, eps, silu, out_f32, pre_bias, passthrough)
 
 
 def _require_nhwc_half(x, what):

@@ -198,9 +198,10 @@ size_t cg_groupnorm_nhwc_workspace_bytes(int N, int HW, int C);
 int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G, const float* gamma, const float* beta, const float* scale_shift,
                           const float* pre_bias, float eps, int silu, int out_f32, void* y, float* stats, float* coef, void* workspace, void* stream);
 /* input gradient of the above (weights are frozen, models.py:67-71 / :120-127): dy [N,HW,C] fp16 (dy_f32 == 0) or fp32,
- * x / stats / coef as given to / produced by the forward -> dx [N,HW,C] fp16. */
+ * x / stats / coef as given to / produced by the forward -> dx [N,HW,C] fp16.  dres [N,HW,C] fp16 or NULL is added to dx: the
+ * gradient that reaches x through its other consumer (the block's residual / skip path), saving autograd's separate accumulation pass. */
 int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, int N, int HW, int C, int G, const float* stats, const float* coef,
-                          const float* pre_bias, int silu, void* dx, void* workspace, void* stream);
+                          const float* pre_bias, int silu, const void* dres, void* dx, void* workspace, void* stream);
 /* ResBlock tail `skip(x) + out_conv(h)` with the convolution biases deferred: out[r,c] = a[r,c] + b[r,c] + bias[c].
  * a, b, out [rows, C] fp16 (NHWC rows = N*H*W), bias [C] fp32, C % 8 == 0.  Its gradient is the identity on a and b. */
 int cg_bias_residual_add_nhwc(const void* a, const void* b, const float* bias, int64_t rows, int C, void* out, void* stream);

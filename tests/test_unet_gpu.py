@@ -35,6 +35,9 @@ CASES = [
     (1, 2048, 8, 8, 32),     # deepest concat: one row lane per CTA
     (1, 1536, 16, 16, 32),   # C/8 = 192
     (3, 256, 33, 31, 32),
+    # > 2 MB per sample: the three-kernel path with the stand-alone finalize kernels (smaller ones fuse it into the apply kernels)
+    (1, 64, 160, 168, 32),
+    (2, 128, 96, 100, 32),
 ]
 
 
@@ -70,7 +73,7 @@ def test_group_norm_nhwc_forward_backward(case, silu, with_ss, out_f32):
     assert _rel(dx.float(), dxr) <= TOL_BWD, _rel(dx.float(), dxr)
 
 
-@pytest.mark.parametrize("case", [(1, 128, 32, 32, 32), (2, 384, 9, 13, 32), (1, 32, 16, 16, 32), (1, 1024, 8, 8, 32)])
+@pytest.mark.parametrize("case", [(1, 128, 32, 32, 32), (2, 384, 9, 13, 32), (1, 32, 16, 16, 32), (1, 1024, 8, 8, 32), (1, 128, 112, 96, 32)])
 def test_group_norm_nhwc_deferred_conv_bias(case):
     """pre_bias: GN(x + b_c) with the producing convolution's bias folded into the statistics / affine (no memory pass)."""
     from clip_diffusion_b200.unet_ops import group_norm_nhwc
@@ -143,6 +146,32 @@ def test_resample2x_rejects_odd_sizes():
 
     with pytest.raises(_lib.ClipGuideError):
         unet_ops.avg_pool2x(torch.zeros(1, 16, 5, 4, device="cuda").half().contiguous(memory_format=torch.channels_last))
+
+
+def test_group_norm_nhwc_passthrough_sums_both_gradients():
+    """passthrough=True: (y, x') with x' an alias of x; d/dx of f(y) + g(x') comes out of ONE backward kernel."""
+    from clip_diffusion_b200.unet_ops import group_norm_nhwc
+
+    g = torch.Generator().manual_seed(11)
+    shape = (2, 64, 24, 20)
+    x = torch.randn(shape, generator=g).half().cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    gamma, beta = (1 + 0.2 * torch.randn(64, generator=g)).cuda(), (0.1 * torch.randn(64, generator=g)).cuda()
+    w1, w2 = torch.randn(shape, generator=g).half().cuda(), torch.randn(shape, generator=g).half().cuda()
+    y, xp = group_norm_nhwc(x, gamma, beta, 32, 1e-5, silu=True, passthrough=True)
+    assert xp.data_ptr() == x.data_ptr()
+    (gx,) = torch.autograd.grad((y * w1).sum() + (xp * w2).sum(), x)
+    xr = x.detach().float().requires_grad_()
+    yr = F.silu(F.group_norm(xr, 32, gamma, beta, 1e-5))
+    (gr,) = torch.autograd.grad((yr * w1.float()).sum() + (xr * w2.float()).sum(), xr)
+    assert _rel(gx.float(), gr) <= TOL_BWD, _rel(gx.float(), gr)
+    # only one of the two outputs used
+    y, xp = group_norm_nhwc(x, gamma, beta, 32, 1e-5, silu=True, passthrough=True)
+    (g1,) = torch.autograd.grad((xp * w2).sum(), x)
+    assert _rel(g1.float(), w2.float()) <= 1e-6
+    y, xp = group_norm_nhwc(x, gamma, beta, 32, 1e-5, silu=True, passthrough=True)
+    (g2,) = torch.autograd.grad((y * w1).sum(), x)
+    (g2r,) = torch.autograd.grad((F.silu(F.group_norm(xr, 32, gamma, beta, 1e-5)) * w1.float()).sum(), xr)
+    assert _rel(g2.float(), g2r) <= TOL_BWD
 
 
 def test_group_norm_nhwc_tokens_and_determinism():

@@ -19,7 +19,8 @@ bench.main()
 OURS = ("gemm_bf16_tn_kernel", "attn_fwd_kernel", "attn_bwd_", "attn_delta_kernel", "ln_fwd_kernel", "ln_bwd_kernel", "tables_kernel",
         "resample_fwd_kernel", "resample_bwd_kernel", "augment_fwd_kernel", "jitter_fwd_kernel", "jitter_bwd_kernel", "affine_bwd_kernel",
         "tv_kernel", "range_kernel", "sph_", "set_cls_kernel", "proj_fwd_kernel", "proj_bwd_kernel", "tokens_to_bf16_kernel", "patchify_kernel",
-        "sumsq_nan_kernel", "finalize_kernel", "nanflag_kernel")
+        "sumsq_nan_kernel", "finalize_kernel", "nanflag_kernel", "gn_stats_partial_kernel", "gn_finalize_", "gn_apply_", "gn_bwd_partial_kernel",
+        "bias_residual_add_kernel", "resample2x_kernel", "concat2_kernel", "gemm_bf16_tn_pair_kernel", "hist_kernel", "count_kernel", "::apply_kernel")
 rows = {}
 for ev in prof.events():
     if ev.device_type.name != "CUDA":
