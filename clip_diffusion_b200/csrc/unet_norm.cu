@@ -38,13 +38,16 @@ static Geo geometry(int N, int HW, int C) {
   g.rows_per_iter = kMaxThreads / g.cvecs;
   if (g.rows_per_iter < 1) g.rows_per_iter = 1;
   g.threads = g.cvecs * g.rows_per_iter;
-  int target = (4 * CG_NUM_SMS) / (N > 0 ? N : 1);
+  // ~8 CTAs per SM (ncu: at 4 the kernels sat at 50 % occupancy and 53 % of DRAM throughput, latency bound), each chunk a whole
+  // number of unrolled iterations so that (almost) no thread runs the one-load-at-a-time tail loop
+  int target = (8 * CG_NUM_SMS) / (N > 0 ? N : 1);
   if (target < 1) target = 1;
   const int min_rows = g.rows_per_iter * kUnroll;
   int max_chunks = HW / min_rows;
   if (max_chunks < 1) max_chunks = 1;
   int chunks = target < max_chunks ? target : max_chunks;
   g.rows_per_chunk = (HW + chunks - 1) / chunks;
+  g.rows_per_chunk = ((g.rows_per_chunk + min_rows - 1) / min_rows) * min_rows;
   g.chunks = (HW + g.rows_per_chunk - 1) / g.rows_per_chunk;
   return g;
 }
@@ -441,8 +444,8 @@ __global__ void __launch_bounds__(kFinalizeThreads) gn_finalize_bwd_kernel(const
   }
 }
 
-template <bool SILU, typename TDy>
-__global__ void __launch_bounds__(kMaxThreads) gn_apply_bwd_kernel(const TDy* __restrict__ dy, const __half* __restrict__ x, int HW, int C, int cvecs,
+template <bool SILU, typename TDy, bool HAS_RES>
+__global__ void __launch_bounds__(kMaxThreads, HAS_RES ? 3 : 4) gn_apply_bwd_kernel(const TDy* __restrict__ dy, const __half* __restrict__ x, int HW, int C, int cvecs,
                                                                     int rows_per_iter, int rows_per_chunk, const float* __restrict__ coefA,
                                                                     const float* __restrict__ coefB, const float* __restrict__ coefBx,
                                                                     const float* __restrict__ coefCx, const __half* __restrict__ dres,
@@ -463,17 +466,17 @@ __global__ void __launch_bounds__(kMaxThreads) gn_apply_bwd_kernel(const TDy* __
   const TDy* gp = dy + off + (size_t)row * C;
   __half* op = dx + off + (size_t)row * C;
   // dres: gradient reaching x through its OTHER consumer (the block's skip path), added here instead of in a separate pass
-  const ptrdiff_t res_off = dres ? (dres - dx) : 0;
+  const ptrdiff_t res_off = HAS_RES ? (dres - dx) : 0;
   auto apply = [&](const Raw8<__half>& xr, const Raw8<TDy>& gr, __half* dst) {
     float xv[8], gv[8], rv[8];
-    if (dres) Row8<__half>::load(dst + res_off, rv);
+    if (HAS_RES) Row8<__half>::load(dst + res_off, rv);
     xr.get(xv);
     gr.get(gv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float dv = dact<SILU>(gv[j], SILU ? fmaf(a[j], xv[j], b[j]) : 0.f);
       gv[j] = fmaf(a[j], dv, fmaf(bx[j], xv[j], cx[j]));
-      if (dres) gv[j] += rv[j];
+      if (HAS_RES) gv[j] += rv[j];
     }
     Row8<__half>::store(dst, gv);
   };
@@ -631,8 +634,12 @@ extern "C" int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, 
     CG_LAUNCH_CHECK();                                                                                                                         \
     gn_finalize_bwd_kernel<<<N * G, kFinalizeThreads, 0, st>>>(partial, g.chunks, C, G, HW, stats, coefA, pre_bias, coefBx, coefCx);           \
     CG_LAUNCH_CHECK();                                                                                                                         \
-    gn_apply_bwd_kernel<S, T><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB, coefBx, \
-                                                          coefCx, (const __half*)dres, (__half*)dx);                                                                \
+    if (dres)                                                                                                                                  \
+      gn_apply_bwd_kernel<S, T, true><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB,   \
+                                                                  coefBx, coefCx, (const __half*)dres, (__half*)dx);                           \
+    else                                                                                                                                       \
+      gn_apply_bwd_kernel<S, T, false><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB,  \
+                                                                   coefBx, coefCx, nullptr, (__half*)dx);                                      \
     CG_LAUNCH_CHECK();                                                                                                                         \
   } while (0)
   if (silu) {
