@@ -41,6 +41,12 @@ __device__ __forceinline__ void mma_bf16(float c[4], const uint32_t a[4], uint32
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// 2^x in ONE MUFU op (exp2f adds range handling; every softmax element pays it and the kernels are issue bound)
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -137,26 +143,32 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) attn_fwd_kernel(const __nv_bfl
       }
     }
     float mx0 = m0, mx1 = m1;
+    if (kc + 64 > T) {  // only the last chunk has keys beyond T (warp-uniform branch)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = kc + nt * 8 + t4 * 2;
+        if (key >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (key + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      }
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const int key = kc + nt * 8 + t4 * 2;
-      if (key >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-      if (key + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float c0 = exp2f((m0 - mx0) * scale_log2), c1 = exp2f((m1 - mx1) * scale_log2);
+    const float c0 = ex2((m0 - mx0) * scale_log2), c1 = ex2((m1 - mx1) * scale_log2);
     m0 = mx0; m1 = mx1;
+    const float nm0 = -m0 * scale_log2, nm1 = -m1 * scale_log2;
     l0 *= c0; l1 *= c1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
     uint32_t pa[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f((s[nt][0] - m0) * scale_log2), p1 = exp2f((s[nt][1] - m0) * scale_log2);
-      const float p2 = exp2f((s[nt][2] - m1) * scale_log2), p3 = exp2f((s[nt][3] - m1) * scale_log2);
+      const float p0 = ex2(fmaf(s[nt][0], scale_log2, nm0)), p1 = ex2(fmaf(s[nt][1], scale_log2, nm0));
+      const float p2 = ex2(fmaf(s[nt][2], scale_log2, nm1)), p3 = ex2(fmaf(s[nt][3], scale_log2, nm1));
       l0 += p0 + p1; l1 += p2 + p3;
       pa[nt >> 1][(nt & 1) * 2] = pack2(p0, p1);
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2, p3);
@@ -243,7 +255,9 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) attn_bwd_dq_kernel(const __nv_
   load_a_frags(sQ, 0, qa);
   load_a_frags(sdO, 0, da);
   const int q0 = r0 + g, q1 = q0 + 8;
-  const float lse0 = q0 < T ? lb[q0] : 0.f, lse1 = q1 < T ? lb[q1] : 0.f;
+  // P = exp(s*scale - lse) = 2^(s*scale*log2e - lse*log2e): one FFMA + one MUFU per element
+  const float sl2 = scale * LOG2E;
+  const float lse0 = q0 < T ? -lb[q0] * LOG2E : 0.f, lse1 = q1 < T ? -lb[q1] * LOG2E : 0.f;
   const float dl0 = q0 < T ? db[q0] : 0.f, dl1 = q1 < T ? db[q1] : 0.f;
   float dq[8][4];
 #pragma unroll
@@ -260,12 +274,16 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) attn_bwd_dq_kernel(const __nv_
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) { mma_bf16(s, qa[kk], bk[kk][0], bk[kk][1]); mma_bf16(dp, da[kk], bv[kk][0], bv[kk][1]); }
       }
-      const int key = kc + nt * 8 + t4 * 2;
-      const bool v0 = key < T, v1 = key + 1 < T;
-      const float p0 = v0 ? __expf(s[0] * scale - lse0) : 0.f, p1 = v1 ? __expf(s[1] * scale - lse0) : 0.f;
-      const float p2 = v0 ? __expf(s[2] * scale - lse1) : 0.f, p3 = v1 ? __expf(s[3] * scale - lse1) : 0.f;
-      dsa[nt >> 1][(nt & 1) * 2] = pack2(p0 * (dp[0] - dl0) * scale, p1 * (dp[1] - dl0) * scale);
-      dsa[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2 * (dp[2] - dl1) * scale, p3 * (dp[3] - dl1) * scale);
+      float p0 = ex2(fmaf(s[0], sl2, lse0)), p1 = ex2(fmaf(s[1], sl2, lse0));
+      float p2 = ex2(fmaf(s[2], sl2, lse1)), p3 = ex2(fmaf(s[3], sl2, lse1));
+      if (kc + 64 > T) {  // keys beyond T exist only in the last chunk
+        const int key = kc + nt * 8 + t4 * 2;
+        if (key >= T) { p0 = 0.f; p2 = 0.f; }
+        if (key + 1 >= T) { p1 = 0.f; p3 = 0.f; }
+      }
+      p0 *= scale; p1 *= scale; p2 *= scale; p3 *= scale;
+      dsa[nt >> 1][(nt & 1) * 2] = pack2(p0 * (dp[0] - dl0), p1 * (dp[1] - dl0));
+      dsa[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2 * (dp[2] - dl1), p3 * (dp[3] - dl1));
     }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -310,7 +328,9 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) attn_bwd_dkv_kernel(const __n
   load_tile(sdO, dctx + (long long)n * T * D + h * HD, D, 0, Tp, T);
   const float* lb = lse + ((long long)n * heads + h) * T;
   const float* db = delta + ((long long)n * heads + h) * T;
-  for (int i = threadIdx.x; i < Tp; i += blockDim.x) { s_lse[i] = i < T ? lb[i] : 0.f; s_dl[i] = i < T ? db[i] : 0.f; }
+  // s_lse holds -lse*log2e so that P^T = 2^(s*scale*log2e + s_lse): one FFMA + one MUFU per element
+  for (int i = threadIdx.x; i < Tp; i += blockDim.x) { s_lse[i] = i < T ? -lb[i] * LOG2E : 0.f; s_dl[i] = i < T ? db[i] : 0.f; }
+  const float sl2 = scale * LOG2E;
   cp_async_wait_all();
   __syncthreads();
   const int g = lane >> 2, t4 = lane & 3;
@@ -338,10 +358,14 @@ __global__ void __launch_bounds__(MAXW * 32, MINB) attn_bwd_dkv_kernel(const __n
         for (int kk = 0; kk < 4; ++kk) { mma_bf16(s, ka[kk], bq[kk][0], bq[kk][1]); mma_bf16(dp, va[kk], bo[kk][0], bo[kk][1]); }
       }
       const int q = qc + nt * 8 + t4 * 2;  // columns of the transposed tile are queries
-      const bool v0 = q < T, v1 = q + 1 < T;
-      const float ls0 = s_lse[q], ls1 = s_lse[q + 1], d0 = s_dl[q], d1 = s_dl[q + 1];
-      const float p0 = v0 ? __expf(s[0] * scale - ls0) : 0.f, p1 = v1 ? __expf(s[1] * scale - ls1) : 0.f;
-      const float p2 = v0 ? __expf(s[2] * scale - ls0) : 0.f, p3 = v1 ? __expf(s[3] * scale - ls1) : 0.f;
+      const float2 ls = *reinterpret_cast<const float2*>(s_lse + q), dd = *reinterpret_cast<const float2*>(s_dl + q);
+      const float ls0 = ls.x, ls1 = ls.y, d0 = dd.x, d1 = dd.y;
+      float p0 = ex2(fmaf(s[0], sl2, ls0)), p1 = ex2(fmaf(s[1], sl2, ls1));
+      float p2 = ex2(fmaf(s[2], sl2, ls0)), p3 = ex2(fmaf(s[3], sl2, ls1));
+      if (qc + 64 > T) {  // queries beyond T exist only in the last chunk
+        if (q >= T) { p0 = 0.f; p2 = 0.f; }
+        if (q + 1 >= T) { p1 = 0.f; p3 = 0.f; }
+      }
       pta[nt >> 1][(nt & 1) * 2] = pack2(p0, p1);
       pta[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2, p3);
       dsta[nt >> 1][(nt & 1) * 2] = pack2(p0 * (dp[0] - d0) * scale, p1 * (dp[1] - d1) * scale);
