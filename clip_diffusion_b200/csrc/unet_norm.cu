@@ -17,6 +17,7 @@
 // levels, four independent loads in flight per thread.  No atomics: partials are reduced in a fixed order => deterministic.
 // Weights are frozen (models.py:120-127 only re-enables grads that never reach the sampler state) => no dgamma/dbeta.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -152,11 +153,22 @@ __device__ __forceinline__ void reduce_rows_and_store(const float* s0, const flo
   }
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------------------------------------------
+// A normalisation is three dependent launches (partial -> finalize -> apply) and most of the UNet's 115 + 115 of them work on
+// maps of a few MB where each kernel runs 3-5 us: launch latency is a third of the op.  The finalize and apply kernels are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization and start with griddepcontrol.wait; their predecessor issues
+// griddepcontrol.launch_dependents at its top, so the dependent grid is scheduled (and its prologue runs) while the
+// predecessor is still streaming, and only the data dependency remains.  CG_PDL=0 falls back to plain stream order.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- forward -----------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(kMaxThreads) gn_stats_partial_kernel(const __half* __restrict__ x, int HW, int C, int cvecs, int rows_per_iter,
                                                                         int rows_per_chunk, float2* __restrict__ partial) {
   __shared__ __align__(16) float red[2 * 2048];
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y, p = blockIdx.x;
   const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
   const int row_end = min(HW, (p + 1) * rows_per_chunk);
@@ -243,6 +255,8 @@ __global__ void __launch_bounds__(kFinalizeThreads) gn_finalize_fwd_kernel(const
   const int total = chunks * cg;
   const float2* base = partial + (size_t)n * chunks * C + g * cg;
   double s = 0.0, q = 0.0;
+  pdl_launch_dependents();
+  pdl_wait();  // the chunk partials of the preceding kernel are complete and visible
   // the loads of one batch are independent: issue four before touching the fp64 accumulators (latency-bound otherwise)
   for (int idx0 = threadIdx.x; idx0 < total; idx0 += 4 * kFinalizeThreads) {
     float2 v[4];
@@ -303,6 +317,8 @@ __global__ void __launch_bounds__(kMaxThreads) gn_apply_fwd_kernel(const __half*
   const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
   const int row_end = min(HW, (p + 1) * rows_per_chunk);
   float a[8], b[8];
+  pdl_launch_dependents();
+  pdl_wait();  // coefficients come from the finalize kernel this one may have been launched ahead of
   load_coef8(coefA + (size_t)n * C + col * 8, a);
   load_coef8(coefB + (size_t)n * C + col * 8, b);
   const size_t off = (size_t)n * HW * C + col * 8;
@@ -348,6 +364,8 @@ __global__ void __launch_bounds__(kMaxThreads) gn_bwd_partial_kernel(const TDy* 
                                                                       int rows_per_iter, int rows_per_chunk, const float* __restrict__ coefA,
                                                                       const float* __restrict__ coefB, float2* __restrict__ partial) {
   __shared__ __align__(16) float red[2 * 2048];
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y, p = blockIdx.x;
   const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
   const int row_end = min(HW, (p + 1) * rows_per_chunk);
@@ -406,6 +424,8 @@ __global__ void __launch_bounds__(kFinalizeThreads) gn_finalize_bwd_kernel(const
                                                                             float* __restrict__ coefCx) {
   __shared__ double red[64];
   const int n = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
+  pdl_launch_dependents();
+  pdl_wait();
   const float mean = stats[2 * blockIdx.x], rstd = stats[2 * blockIdx.x + 1];
   const int total = chunks * cg;
   const float2* base = partial + (size_t)n * chunks * C + g * cg;
@@ -454,6 +474,8 @@ __global__ void __launch_bounds__(kMaxThreads, HAS_RES ? 3 : 4) gn_apply_bwd_ker
   const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
   const int row_end = min(HW, (p + 1) * rows_per_chunk);
   float a[8], b[8], bx[8], cx[8];
+  pdl_launch_dependents();
+  pdl_wait();
   load_coef8(coefA + (size_t)n * C + col * 8, a);
   if (SILU) load_coef8(coefB + (size_t)n * C + col * 8, b);
   load_coef8(coefBx + (size_t)n * C + col * 8, bx);
@@ -505,6 +527,8 @@ __global__ void __launch_bounds__(kMaxThreads, HAS_RES ? 3 : 4) gn_apply_bwd_ker
 // out = a + b + bias_c : the ResBlock's `skip(x) + out_conv(h)` with both convolutions' biases deferred into this one pass
 __global__ void __launch_bounds__(256) bias_residual_add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const float* __restrict__ bias,
                                                                  long long nvec, int cvecs, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float x[8], y[8], bb[8];
     Row8<__half>::load(a + i * 8, x);
@@ -522,6 +546,8 @@ template <bool UP>
 __global__ void __launch_bounds__(256) resample2x_kernel(const __half* __restrict__ x, int Ho, int Wo, int cvecs, long long nvec, float scale,
                                                           __half* __restrict__ y) {
   const int Wi = UP ? Wo / 2 : Wo * 2, Hi = UP ? Ho / 2 : Ho * 2;
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvecs);
     long long pix = i / cvecs;
@@ -555,6 +581,8 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256) concat2_kernel(uint4* __restrict__ a, int ca, uint4* __restrict__ b, int cb, long long nvec,
                                                        uint4* __restrict__ cat) {
   const int ct = ca + cb;
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / ct;
     const int cv = (int)(i - r * ct);
@@ -562,6 +590,31 @@ __global__ void __launch_bounds__(256) concat2_kernel(uint4* __restrict__ a, int
     if (SPLIT) *part = __ldg(cat + i);
     else cat[i] = __ldg(part);
   }
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CG_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Launch `kernel` as a programmatic dependent of the previous kernel in the stream (plain launch when CG_PDL=0).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 int check_shape(int N, int HW, int C, int G) {
@@ -594,12 +647,12 @@ extern "C" int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G,
   float* coefB = coef + (size_t)N * C;
   const dim3 grid(g.chunks, N);
   const __half* xh = (const __half*)x;
-  gn_stats_partial_kernel<<<grid, g.threads, 0, st>>>(xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, partial);
-  CG_LAUNCH_CHECK();
-  gn_finalize_fwd_kernel<<<N * G, kFinalizeThreads, 0, st>>>(partial, g.chunks, C, G, HW, gamma, beta, scale_shift, pre_bias, eps, stats, coefA, coefB);
-  CG_LAUNCH_CHECK();
-#define CG_GN_APPLY(S, T) \
-  gn_apply_fwd_kernel<S, T><<<grid, g.threads, 0, st>>>(xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB, (T*)y)
+  CG_CUDA(launch_dependent(gn_stats_partial_kernel, grid, dim3(g.threads), st, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, partial));
+  CG_CUDA(launch_dependent(gn_finalize_fwd_kernel, dim3(N * G), dim3(kFinalizeThreads), st, (const float2*)partial, g.chunks, C, G, HW, gamma, beta,
+                           scale_shift, pre_bias, eps, stats, coefA, coefB));
+#define CG_GN_APPLY(S, T)                                                                                                            \
+  CG_CUDA(launch_dependent(gn_apply_fwd_kernel<S, T>, grid, dim3(g.threads), st, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, \
+                           (const float*)coefA, (const float*)coefB, (T*)y))
   if (silu) {
     if (out_f32) CG_GN_APPLY(true, float);
     else CG_GN_APPLY(true, __half);
@@ -630,17 +683,17 @@ extern "C" int cg_groupnorm_nhwc_bwd(const void* dy, int dy_f32, const void* x, 
   const __half* xh = (const __half*)x;
 #define CG_GN_BWD(S, T)                                                                                                                        \
   do {                                                                                                                                         \
-    gn_bwd_partial_kernel<S, T><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB, partial); \
-    CG_LAUNCH_CHECK();                                                                                                                         \
-    gn_finalize_bwd_kernel<<<N * G, kFinalizeThreads, 0, st>>>(partial, g.chunks, C, G, HW, stats, coefA, pre_bias, coefBx, coefCx);           \
-    CG_LAUNCH_CHECK();                                                                                                                         \
+    CG_CUDA(launch_dependent(gn_bwd_partial_kernel<S, T>, grid, dim3(g.threads), st, (const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter,          \
+                             g.rows_per_chunk, coefA, coefB, partial));                                                                        \
+    CG_CUDA(launch_dependent(gn_finalize_bwd_kernel, dim3(N * G), dim3(kFinalizeThreads), st, (const float2*)partial, g.chunks, C, G, HW, stats, \
+                             coefA, pre_bias, coefBx, coefCx));                                                                                \
     if (dres)                                                                                                                                  \
-      gn_apply_bwd_kernel<S, T, true><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB,   \
-                                                                  coefBx, coefCx, (const __half*)dres, (__half*)dx);                           \
+      CG_CUDA(launch_dependent(gn_apply_bwd_kernel<S, T, true>, grid, dim3(g.threads), st, (const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter,  \
+                               g.rows_per_chunk, coefA, coefB, (const float*)coefBx, (const float*)coefCx, (const __half*)dres, (__half*)dx)); \
     else                                                                                                                                       \
-      gn_apply_bwd_kernel<S, T, false><<<grid, g.threads, 0, st>>>((const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, coefA, coefB,  \
-                                                                   coefBx, coefCx, nullptr, (__half*)dx);                                      \
-    CG_LAUNCH_CHECK();                                                                                                                         \
+      CG_CUDA(launch_dependent(gn_apply_bwd_kernel<S, T, false>, grid, dim3(g.threads), st, (const T*)dy, xh, HW, C, g.cvecs, g.rows_per_iter, \
+                               g.rows_per_chunk, coefA, coefB, (const float*)coefBx, (const float*)coefCx, (const __half*)nullptr,             \
+                               (__half*)dx));                                                                                                  \
   } while (0)
   if (silu) {
     if (dy_f32) CG_GN_BWD(true, float);
@@ -661,8 +714,8 @@ extern "C" int cg_bias_residual_add_nhwc(const void* a, const void* b, const flo
   const long long nvec = (long long)rows * (C / 8);
   long long blocks = (nvec + 255) / 256;
   if (blocks > 16 * CG_NUM_SMS) blocks = 16 * CG_NUM_SMS;
-  bias_residual_add_kernel<<<(int)blocks, 256, 0, cg_stream(stream)>>>((const __half*)a, (const __half*)b, bias, nvec, C / 8, (__half*)out);
-  CG_LAUNCH_CHECK();
+  CG_CUDA(launch_dependent(bias_residual_add_kernel, dim3((unsigned)blocks), dim3(256), cg_stream(stream), (const __half*)a, (const __half*)b, bias, nvec,
+                           C / 8, (__half*)out));
   return 0;
 }
 
@@ -675,9 +728,12 @@ extern "C" int cg_resample2x_nhwc(const void* x, int N, int H, int W, int C, int
   const long long nvec = (long long)N * Ho * Wo * (C / 8);
   long long blocks = (nvec + 255) / 256;
   if (blocks > 16 * CG_NUM_SMS) blocks = 16 * CG_NUM_SMS;
-  if (up) resample2x_kernel<true><<<(int)blocks, 256, 0, cg_stream(stream)>>>((const __half*)x, Ho, Wo, C / 8, nvec, scale, (__half*)y);
-  else resample2x_kernel<false><<<(int)blocks, 256, 0, cg_stream(stream)>>>((const __half*)x, Ho, Wo, C / 8, nvec, scale, (__half*)y);
-  CG_LAUNCH_CHECK();
+  if (up)
+    CG_CUDA(launch_dependent(resample2x_kernel<true>, dim3((unsigned)blocks), dim3(256), cg_stream(stream), (const __half*)x, Ho, Wo, C / 8, nvec, scale,
+                             (__half*)y));
+  else
+    CG_CUDA(launch_dependent(resample2x_kernel<false>, dim3((unsigned)blocks), dim3(256), cg_stream(stream), (const __half*)x, Ho, Wo, C / 8, nvec, scale,
+                             (__half*)y));
   return 0;
 }
 
@@ -689,8 +745,11 @@ extern "C" int cg_concat2_nhwc(void* a, int Ca, void* b, int Cb, int64_t rows, v
   const long long nvec = (long long)rows * ((Ca + Cb) / 8);
   long long blocks = (nvec + 255) / 256;
   if (blocks > 16 * CG_NUM_SMS) blocks = 16 * CG_NUM_SMS;
-  if (split) concat2_kernel<true><<<(int)blocks, 256, 0, cg_stream(stream)>>>((uint4*)a, Ca / 8, (uint4*)b, Cb / 8, nvec, (uint4*)cat);
-  else concat2_kernel<false><<<(int)blocks, 256, 0, cg_stream(stream)>>>((uint4*)a, Ca / 8, (uint4*)b, Cb / 8, nvec, (uint4*)cat);
-  CG_LAUNCH_CHECK();
+  if (split)
+    CG_CUDA(launch_dependent(concat2_kernel<true>, dim3((unsigned)blocks), dim3(256), cg_stream(stream), (uint4*)a, Ca / 8, (uint4*)b, Cb / 8, nvec,
+                             (uint4*)cat));
+  else
+    CG_CUDA(launch_dependent(concat2_kernel<false>, dim3((unsigned)blocks), dim3(256), cg_stream(stream), (uint4*)a, Ca / 8, (uint4*)b, Cb / 8, nvec,
+                             (uint4*)cat));
   return 0;
 }
