@@ -1,9 +1,15 @@
-"""Stock-PyTorch ADM UNet (the guided-diffusion epsilon model) -- the REPLICATED part of a guidance step.
+"""ADM UNet (the guided-diffusion epsilon model) -- the REPLICATED part of a guidance step.
 
-north_star keeps "the guided-diffusion UNet epsilon forward" replicated and in stock PyTorch; it is needed here
-only as the workload around the CLIP-guidance kernels (clip_diffusion/models.py:87-131 builds it from the
-un-vendored crowsonkb/guided-diffusion; SURVEY.md App. A.3 restates the architecture).  Nothing in this file is a
-kernel target: convolutions, GroupNorm and attention are torch / cuDNN library calls.
+north_star keeps "the guided-diffusion UNet epsilon forward" replicated on every rank; it is the workload around the
+CLIP-guidance kernels (clip_diffusion/models.py:87-131 builds it from the un-vendored crowsonkb/guided-diffusion;
+SURVEY.md App. A.3 restates the architecture) and, once the CLIP side ran on tensor cores, most of the step.
+
+Two execution paths of the same modules and the same state dict:
+  * stock PyTorch (CPU fp32 = the oracle / reference arm's model; CUDA fp16 NCHW kept for A/B): torch / cuDNN library calls only;
+  * ``create_unet(channels_last=True)`` (default for CUDA fp16): NHWC trunk -- convolutions and the UNet's own attention stay
+    cuDNN / cuBLAS calls, everything between them runs on the hand-written NHWC kernels of csrc/unet_norm.cu
+    (clip_diffusion_b200.unet_ops: fused GroupNorm32+scale-shift+SiLU forward / input gradient with deferred conv biases and
+    in-kernel skip-gradient sum, bias+residual add, 2x resample, skip concat / split).  No fallback: it raises without the library.
 
 512 config (models.py:95-116): model_channels 256, 2 res blocks, head_channels 64, attention at 32/16/8,
 channel_mult (0.5,1,1,2,2,4,4), resblock_updown, scale-shift norm, learn_sigma (6 output channels), fp16 trunk.
@@ -23,8 +29,8 @@ class _SplitStatsGroupNorm(torch.autograd.Function):
     Here every group is split into S contiguous chunks whose mean/variance come from one `var_mean` over N*G*S rows and
     are merged exactly (parallel-variance formula, fp32); normalisation is one `addcmul` (fp32 math, one rounding), and the
     backward uses the closed form dx = a_c*dy + b_g*x + c_g with two per-channel reductions and two element-wise passes.
-    A dimension-based fallback handles non-contiguous layouts (channels_last was measured: ATen's NHWC reductions cost more
-    than the cuDNN NCHW<->NHWC transposes they save -- 67 vs 63 ms/step -- so NCHW stays the default)."""
+    A dimension-based fallback handles non-contiguous layouts.  This is the NCHW A/B variant (`bench.py --unet-layout nchw`,
+    61.8 ms/step); the default CUDA path is the NHWC trunk on csrc/unet_norm.cu (23.0 ms/step)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, groups, eps):
