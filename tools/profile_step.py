@@ -32,7 +32,7 @@ total = sum(v[1] for v in rows.values())
 print("# workload %s: device time of one timed step = %.3f ms over %d kernel/memcpy records" % (wl, total / 1e3, sum(v[0] for v in rows.values())))
 print("# %-7s %-6s %-10s name" % ("share", "calls", "total_us"))
 mine = 0.0
-for name, (n, us) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:45]:
+for name, (n, us) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:(10000 if os.environ.get("PROFILE_ALL") else 45)]:
     print("%6.2f%% %6d %10.1f  %s" % (100 * us / total, n, us, name[:150]))
 for name, (n, us) in rows.items():
     if any(k in name for k in OURS):
