@@ -114,6 +114,18 @@ def test_diffusion_schedule_and_unet():
     assert abs(n512 / 1e6 - 558.0) < 0.1 and abs(n256 / 1e6 - 552.8) < 0.1  # SURVEY.md App. A.3 parameter counts
 
 
+def test_groupnorm_workspace_query_is_host_only_and_sane():
+    """cg_groupnorm_nhwc_workspace_bytes needs no GPU: chunk partials (float2 per channel and chunk) + two coefficient rows."""
+    from clip_diffusion_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.cg_groupnorm_nhwc_workspace_bytes(1, 64, 12) == 0 and lib.cg_groupnorm_nhwc_workspace_bytes(0, 64, 16) == 0  # C % 8, N < 1
+    small, big = lib.cg_groupnorm_nhwc_workspace_bytes(1, 64, 1024), lib.cg_groupnorm_nhwc_workspace_bytes(1, 512 * 512, 128)
+    assert small >= 2 * 1024 * 4 + 1024 * 8 and big >= 2 * 128 * 4 + 128 * 8
+    assert big <= 16 << 20  # bounded: ~8 chunks per SM at most
+    assert lib.cg_groupnorm_nhwc_workspace_bytes(2, 4096, 256) % 16 == 0
+
+
 def test_group_norm32_stock_path_spells_the_resblock_arithmetic():
     """GroupNorm32(x, scale_shift, silu) on the CPU / fp32 path == silu(GN(x) * (1 + scale) + shift) (guided-diffusion ResBlock)."""
     from torch.nn import functional as Fn
