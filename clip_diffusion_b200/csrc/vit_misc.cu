@@ -74,15 +74,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   s1 = warp_sum(s1) / (float)D;
   s2 = warp_sum(s2) / (float)D;
   float4* dxr = reinterpret_cast<float4*>(dx + (long long)row * row_stride);
+  // finish r in place (x^ is dead afterwards), THEN fetch the whole previous-gradient row in one batch into the freed registers:
+  // as a load -> add -> store per float4 the accumulate path was NV serialised DRAM round trips per row
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-      float4 r;
-      r.x = rstd * (dh[i].x - s1 - xh[i].x * s2); r.y = rstd * (dh[i].y - s1 - xh[i].y * s2);
-      r.z = rstd * (dh[i].z - s1 - xh[i].z * s2); r.w = rstd * (dh[i].w - s1 - xh[i].w * s2);
-      if (accumulate) { const float4 p = dxr[i * 32 + lane]; r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w; }
-      dxr[i * 32 + lane] = r;
-      if (dxb) reinterpret_cast<uint2*>(dxb + (long long)row * row_stride)[i * 32 + lane] = make_uint2(pack2(r.x, r.y), pack2(r.z, r.w));
-    }
+    dh[i].x = rstd * (dh[i].x - s1 - xh[i].x * s2); dh[i].y = rstd * (dh[i].y - s1 - xh[i].y * s2);
+    dh[i].z = rstd * (dh[i].z - s1 - xh[i].z * s2); dh[i].w = rstd * (dh[i].w - s1 - xh[i].w * s2);
+  }
+  if (accumulate) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(xh[i].x), "=f"(xh[i].y), "=f"(xh[i].z), "=f"(xh[i].w) : "l"(dxr + i * 32 + lane));
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { dh[i].x += xh[i].x; dh[i].y += xh[i].y; dh[i].z += xh[i].z; dh[i].w += xh[i].w; }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    dxr[i * 32 + lane] = dh[i];
+    if (dxb) reinterpret_cast<uint2*>(dxb + (long long)row * row_stride)[i * 32 + lane] = make_uint2(pack2(dh[i].x, dh[i].y), pack2(dh[i].z, dh[i].w));
+  }
 }
 
 __global__ void set_cls_kernel(const float* __restrict__ cls, const float* __restrict__ pos, int T, int D, float* __restrict__ x) {
