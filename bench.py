@@ -249,7 +249,7 @@ def main():
     from clip_diffusion_b200.unet import create_unet, graph_unet
     from clip_diffusion_b200.utils.functional import set_seed
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / debug lines go to stderr: rank 0's stdout is exactly one JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     torch.backends.cudnn.benchmark = os.environ.get("CG_CUDNN_BENCHMARK", "1") == "1"  # let cuDNN pick conv algorithms for the static UNet shapes
