@@ -249,7 +249,8 @@ def main():
     from clip_diffusion_b200.unet import create_unet, graph_unet
     from clip_diffusion_b200.utils.functional import set_seed
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / debug lines go to stderr: rank 0's stdout is exactly one JSON line
+    # (the image exports NCCL_DEBUG=VERSION: NCCL prints its one-line version banner on rank 0's stdout before the JSON line; it is
+    # left alone -- the JSON line is always the LAST line of stdout)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     torch.backends.cudnn.benchmark = os.environ.get("CG_CUDNN_BENCHMARK", "1") == "1"  # let cuDNN pick conv algorithms for the static UNet shapes
