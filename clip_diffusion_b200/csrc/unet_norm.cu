@@ -592,6 +592,89 @@ __global__ void __launch_bounds__(256) concat2_kernel(uint4* __restrict__ a, int
   }
 }
 
+// ---- producers that also emit the NEXT normalisation's chunk partials -----------------------------------------------------------------
+// The tensor a ResBlock returns (bias + residual add) and the skip concatenation are exactly what the following block's in_norm
+// reduces first.  These variants run in the GroupNorm geometry (CTA = row chunk, thread = channel octet) and, while streaming the
+// result out, accumulate sum / sum of squares of the fp16-ROUNDED values they store -- the same numbers gn_stats_partial_kernel
+// would read back -- so that normalisation starts at its finalize kernel (one full read of the activation saved per block).
+template <bool CONCAT>
+__global__ void __launch_bounds__(kMaxThreads) producer_stats_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
+                                                                      const float* __restrict__ bias, int ca, int HW, int C, int cvecs,
+                                                                      int rows_per_iter, int rows_per_chunk, __half* __restrict__ out,
+                                                                      float2* __restrict__ partial) {
+  __shared__ __align__(16) float red[2 * 2048];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.y, p = blockIdx.x;
+  const int col = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
+  const int row_end = min(HW, (p + 1) * rows_per_chunk);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  auto account = [&](const uint4& packed) {
+    float v[8];
+    unpack8(packed, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += v[j];
+      q[j] = fmaf(v[j], v[j], q[j]);
+    }
+  };
+  int row = p * rows_per_chunk + r;
+  __half* optr = out + ((size_t)n * HW + row) * C + col * 8;
+  const size_t ostride = (size_t)rows_per_iter * C;
+  if (CONCAT) {
+    // a [N,HW,ca] | b [N,HW,C-ca]: this thread's octet comes from one of them for its whole life
+    const bool from_a = col * 8 < ca;
+    const int cs = from_a ? ca : C - ca;
+    const __half* src = (from_a ? a + col * 8 : b + (col * 8 - ca)) + ((size_t)n * HW + row) * cs;
+    const size_t sstride = (size_t)rows_per_iter * cs;
+    for (; row + (kUnroll - 1) * rows_per_iter < row_end; row += kUnroll * rows_per_iter, src += kUnroll * sstride, optr += kUnroll * ostride) {
+      uint4 raw[kUnroll];
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) raw[k] = ldg_stream(src + k * sstride);
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        *reinterpret_cast<uint4*>(optr + k * ostride) = raw[k];
+        account(raw[k]);
+      }
+    }
+    for (; row < row_end; row += rows_per_iter, src += sstride, optr += ostride) {
+      const uint4 raw = ldg_stream(src);
+      *reinterpret_cast<uint4*>(optr) = raw;
+      account(raw);
+    }
+  } else {
+    float bb[8];
+    load_coef8(bias + col * 8, bb);
+    const __half* ap = a + ((size_t)n * HW + row) * C + col * 8;
+    const __half* bp = b + ((size_t)n * HW + row) * C + col * 8;
+    constexpr int U = 2;
+    auto emit = [&](const uint4& xa, const uint4& xb, __half* dst) {
+      float x[8], y[8];
+      unpack8(xa, x);
+      unpack8(xb, y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = x[j] + y[j] + bb[j];
+      const uint4 packed = pack8(x);
+      *reinterpret_cast<uint4*>(dst) = packed;
+      account(packed);
+    };
+    for (; row + (U - 1) * rows_per_iter < row_end; row += U * rows_per_iter, ap += U * ostride, bp += U * ostride, optr += U * ostride) {
+      uint4 xa[U], xb[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        xa[k] = ldg_stream(ap + k * ostride);
+        xb[k] = ldg_stream(bp + k * ostride);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) emit(xa[k], xb[k], optr + k * ostride);
+    }
+    for (; row < row_end; row += rows_per_iter, ap += ostride, bp += ostride, optr += ostride) emit(ldg_stream(ap), ldg_stream(bp), optr);
+  }
+  reduce_rows_and_store(s, q, C, cvecs, rows_per_iter, red, partial + ((size_t)n * gridDim.x + p) * C);
+}
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -635,19 +718,21 @@ extern "C" size_t cg_groupnorm_nhwc_workspace_bytes(int N, int HW, int C) {
 }
 
 extern "C" int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G, const float* gamma, const float* beta, const float* scale_shift,
-                                     const float* pre_bias, float eps, int silu, int out_f32, void* y, float* stats, float* coef, void* workspace,
-                                     void* stream) {
+                                     const float* pre_bias, const void* input_partial, float eps, int silu, int out_f32, void* y, float* stats,
+                                     float* coef, void* workspace, void* stream) {
   if (int rc = check_shape(N, HW, C, G)) return rc;
   CG_REQUIRE(x && y && gamma && beta && stats && coef && workspace, "groupnorm_nhwc_fwd: null pointer");
   CG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)coef & 15) == 0, "groupnorm_nhwc_fwd: buffers must be 16-byte aligned");
   const Geo g = geometry(N, HW, C);
   cudaStream_t st = cg_stream(stream);
-  float2* partial = (float2*)workspace;
+  // input_partial: the chunk partials of x, already written by the kernel that produced x (cg_*_stats_nhwc) -> no statistics pass
+  float2* partial = input_partial ? (float2*)input_partial : (float2*)workspace;
   float* coefA = coef;
   float* coefB = coef + (size_t)N * C;
   const dim3 grid(g.chunks, N);
   const __half* xh = (const __half*)x;
-  CG_CUDA(launch_dependent(gn_stats_partial_kernel, grid, dim3(g.threads), st, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, partial));
+  if (!input_partial)
+    CG_CUDA(launch_dependent(gn_stats_partial_kernel, grid, dim3(g.threads), st, xh, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, partial));
   CG_CUDA(launch_dependent(gn_finalize_fwd_kernel, dim3(N * G), dim3(kFinalizeThreads), st, (const float2*)partial, g.chunks, C, G, HW, gamma, beta,
                            scale_shift, pre_bias, eps, stats, coefA, coefB));
 #define CG_GN_APPLY(S, T)                                                                                                            \
@@ -751,5 +836,31 @@ extern "C" int cg_concat2_nhwc(void* a, int Ca, void* b, int Cb, int64_t rows, v
   else
     CG_CUDA(launch_dependent(concat2_kernel<false>, dim3((unsigned)blocks), dim3(256), cg_stream(stream), (uint4*)a, Ca / 8, (uint4*)b, Cb / 8, nvec,
                              (uint4*)cat));
+  return 0;
+}
+
+extern "C" int cg_bias_residual_add_stats_nhwc(const void* a, const void* b, const float* bias, int N, int HW, int C, void* out, void* partial,
+                                               void* stream) {
+  if (int rc = check_shape(N, HW, C, 1)) return rc;
+  CG_REQUIRE(a && b && bias && out && partial, "bias_residual_add_stats_nhwc: null pointer");
+  CG_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)bias & 15) == 0 &&
+                 ((uintptr_t)partial & 15) == 0,
+             "bias_residual_add_stats_nhwc: buffers must be 16-byte aligned");
+  const Geo g = geometry(N, HW, C);
+  CG_CUDA(launch_dependent(producer_stats_kernel<false>, dim3(g.chunks, N), dim3(g.threads), cg_stream(stream), (const __half*)a, (const __half*)b, bias, 0,
+                           HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, (__half*)out, (float2*)partial));
+  return 0;
+}
+
+extern "C" int cg_concat2_stats_nhwc(const void* a, int Ca, const void* b, int Cb, int N, int HW, void* cat, void* partial, void* stream) {
+  CG_REQUIRE(Ca >= 8 && Cb >= 8 && Ca % 8 == 0 && Cb % 8 == 0, "concat2_stats_nhwc: Ca=%d Cb=%d (channel counts must be multiples of 8)", Ca, Cb);
+  if (int rc = check_shape(N, HW, Ca + Cb, 1)) return rc;
+  CG_REQUIRE(a && b && cat && partial, "concat2_stats_nhwc: null pointer");
+  CG_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)cat & 15) == 0 && ((uintptr_t)partial & 15) == 0,
+             "concat2_stats_nhwc: buffers must be 16-byte aligned");
+  const int C = Ca + Cb;
+  const Geo g = geometry(N, HW, C);
+  CG_CUDA(launch_dependent(producer_stats_kernel<true>, dim3(g.chunks, N), dim3(g.threads), cg_stream(stream), (const __half*)a, (const __half*)b,
+                           (const float*)nullptr, Ca, HW, C, g.cvecs, g.rows_per_iter, g.rows_per_chunk, (__half*)cat, (float2*)partial));
   return 0;
 }

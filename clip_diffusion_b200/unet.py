@@ -99,14 +99,17 @@ class GroupNorm32(nn.GroupNorm):
 
     nhwc = False
 
-    def forward(self, x, scale_shift=None, silu=False, out_dtype=None, pre_bias=None, passthrough=False):
+    def forward(self, x, scale_shift=None, silu=False, out_dtype=None, pre_bias=None, passthrough=False, input_partial=None):
         if self.nhwc and x.is_cuda and x.dtype == torch.float16:
             from clip_diffusion_b200.unet_ops import group_norm_nhwc
+
+            if input_partial is None:  # statistics partials written by the op that produced x (bias_residual_add / concat_channels)
+                input_partial = getattr(x, "_gn_partial", None)
 
             if x.dim() == 4 and not x.is_contiguous(memory_format=torch.channels_last):
                 x = x.contiguous(memory_format=torch.channels_last)
             return group_norm_nhwc(x, self.weight, self.bias, self.num_groups, self.eps, scale_shift=scale_shift, silu=silu, out_dtype=out_dtype,
-                                   pre_bias=pre_bias, passthrough=passthrough)
+                                   pre_bias=pre_bias, passthrough=passthrough, input_partial=input_partial)
         assert not passthrough, "passthrough is a feature of the fused NHWC op"
         if pre_bias is not None:
             x = x + pre_bias.type(x.dtype).view(1, -1, *([1] * (x.dim() - 2)))
@@ -192,7 +195,7 @@ class ResBlock(nn.Module):
         h = self.out_norm(h, scale_shift=ss, silu=True, pre_bias=b_in)
         h = F.conv2d(h, self.out_conv.weight, None, padding=1)
         skip = x if isinstance(self.skip, nn.Identity) else F.conv2d(x, self.skip.weight, None)
-        return bias_residual_add(h, skip, b_tail)
+        return bias_residual_add(h, skip, b_tail, stats=True)  # whatever consumes a block's output normalises it first
 
 
 class AttentionBlock(nn.Module):
@@ -223,7 +226,7 @@ class AttentionBlock(nn.Module):
             x = x.contiguous(memory_format=torch.channels_last)
         t = hh * ww
         tok = x.permute(0, 2, 3, 1).reshape(b, t, c)  # a view
-        normed, tok = self.norm(tok, passthrough=True)
+        normed, tok = self.norm(tok, passthrough=True, input_partial=getattr(x, "_gn_partial", None))
         qkv = F.linear(normed, self.qkv.weight.squeeze(-1), self.qkv.bias)
         q, k, v = qkv.view(b, t, self.heads, 3, c // self.heads).permute(3, 0, 2, 1, 4)
         a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, t, c)
@@ -331,7 +334,7 @@ class UNetModel(nn.Module):
         if fused:
             from clip_diffusion_b200.unet_ops import concat_channels
         for blk in self.output_blocks:
-            h = blk(concat_channels(h, hs.pop()) if fused else torch.cat([h, hs.pop()], dim=1), emb)
+            h = blk(concat_channels(h, hs.pop(), stats=True) if fused else torch.cat([h, hs.pop()], dim=1), emb)
         if self.channels_last and h.is_cuda and h.dtype == torch.float16:
             h = self.out_norm(h, silu=True, out_dtype=x.dtype)  # fp32 statistics and fp32 output from the fp16 trunk, one pass
         else:

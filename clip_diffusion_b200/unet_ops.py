@@ -33,7 +33,7 @@ def _like_layout(x, t):
 
 class _GroupNormNHWC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, silu, out_f32, pre_bias, passthrough):
+    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, silu, out_f32, pre_bias, passthrough, input_partial=None):
         _lib.require_cuda(x, gamma, beta, scale_shift, pre_bias)
         if x.dtype != torch.float16:
             raise _lib.ClipGuideError("group_norm_nhwc: fp16 activations expected, got %s" % x.dtype)
@@ -53,7 +53,7 @@ class _GroupNormNHWC(torch.autograd.Function):
         coef = torch.empty(2, N, C, device=x.device, dtype=torch.float32)
         ws = torch.empty(_lib.load().cg_groupnorm_nhwc_workspace_bytes(N, HW, C), device=x.device, dtype=torch.uint8)
         _lib.call("cg_groupnorm_nhwc_fwd", _lib.ptr(x), N, HW, C, int(groups), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(scale_shift),
-                  _lib.ptr(pre_bias), float(eps), int(bool(silu)), int(bool(out_f32)), _lib.ptr(y), _lib.ptr(stats), _lib.ptr(coef), _lib.ptr(ws))
+                  _lib.ptr(pre_bias), _lib.ptr(input_partial), float(eps), int(bool(silu)), int(bool(out_f32)), _lib.ptr(y), _lib.ptr(stats), _lib.ptr(coef), _lib.ptr(ws))
         ctx.save_for_backward(x, stats, coef, pre_bias)
         ctx.cfg = (N, HW, C, int(groups), int(bool(silu)), bool(out_f32))
         ctx.set_materialize_grads(False)  # an unused output's gradient arrives as None, not as a zero tensor
@@ -68,7 +68,7 @@ class _GroupNormNHWC(torch.autograd.Function):
         x, stats, coef, pre_bias = ctx.saved_tensors
         N, HW, C, groups, silu, out_f32 = ctx.cfg
         if dy is None:  # only the pass-through output was used
-            return (dres,) + (None,) * 9
+            return (dres,) + (None,) * 10
         dy = _like_layout(x, dy)
         if dy.dtype not in (torch.float16, torch.float32):
             dy = dy.float()
@@ -78,19 +78,26 @@ class _GroupNormNHWC(torch.autograd.Function):
         ws = torch.empty(_lib.load().cg_groupnorm_nhwc_workspace_bytes(N, HW, C), device=x.device, dtype=torch.uint8)
         _lib.call("cg_groupnorm_nhwc_bwd", _lib.ptr(dy), int(dy.dtype == torch.float32), _lib.ptr(x), N, HW, C, groups, _lib.ptr(stats),
                   _lib.ptr(coef), _lib.ptr(pre_bias), silu, _lib.ptr(dres), _lib.ptr(dx), _lib.ptr(ws))
-        return (dx,) + (None,) * 9
+        return (dx,) + (None,) * 10
 
 
-def group_norm_nhwc(x, gamma, beta, groups=32, eps=1e-5, scale_shift=None, silu=False, out_dtype=None, pre_bias=None, passthrough=False):
+def group_norm_nhwc(x, gamma, beta, groups=32, eps=1e-5, scale_shift=None, silu=False, out_dtype=None, pre_bias=None, passthrough=False,
+                    input_partial=None):
     """act(GroupNorm32(x + pre_bias) * (1 + scale) + shift) for x [N,C,H,W] channels_last (or [N,T,C]) fp16 on CUDA.
 
     scale_shift: [N, 2C] (the ResBlock's embedding projection, scale | shift) or None; silu: apply SiLU;
     out_dtype: torch.float16 (default) or torch.float32 (the UNet's fp32 output head);
     pre_bias: [C] bias of the convolution that produced x, deferred into this op (no extra memory pass);
     passthrough: return (y, x') with x' an alias of x to be used by the block's residual / skip path -- the two gradients of x are
-    then summed inside the backward kernel."""
+    then summed inside the backward kernel;
+    input_partial: the chunk partials of x written by the op that produced it (`bias_residual_add` / `concat_channels` attach them
+    to their result as `._gn_partial`): the statistics pass over x is skipped."""
     out_f32 = out_dtype == torch.float32
-    return _GroupNormNHWC.apply(x, gamma, beta, scale_shift, groups, eps, silu, out_f32, pre_bias, passthrough)
+    if input_partial is not None:
+        N, HW, C = _nhwc_dims(x)
+        if input_partial.numel() != _lib.load().cg_groupnorm_nhwc_workspace_bytes(N, HW, C):
+            raise ValueError("input_partial does not belong to a tensor of this shape")
+    return _GroupNormNHWC.apply(x, gamma, beta, scale_shift, groups, eps, silu, out_f32, pre_bias, passthrough, input_partial)
 
 
 def _require_nhwc_half(x, what):
@@ -101,7 +108,7 @@ def _require_nhwc_half(x, what):
 
 class _BiasResidualAdd(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b, bias):
+    def forward(ctx, a, b, bias, partial):
         a, b = _require_nhwc_half(a, "bias_residual_add"), _require_nhwc_half(b, "bias_residual_add")
         if a.shape != b.shape:
             raise ValueError("shape mismatch: %s vs %s" % (tuple(a.shape), tuple(b.shape)))
@@ -110,17 +117,31 @@ class _BiasResidualAdd(torch.autograd.Function):
         if bias.numel() != C:
             raise ValueError("bias must have C = %d elements" % C)
         out = torch.empty_like(a)
-        _lib.call("cg_bias_residual_add_nhwc", _lib.ptr(a), _lib.ptr(b), _lib.ptr(bias), N * H * W, C, _lib.ptr(out))
+        if partial is None:
+            _lib.call("cg_bias_residual_add_nhwc", _lib.ptr(a), _lib.ptr(b), _lib.ptr(bias), N * H * W, C, _lib.ptr(out))
+        else:
+            _lib.call("cg_bias_residual_add_stats_nhwc", _lib.ptr(a), _lib.ptr(b), _lib.ptr(bias), N, H * W, C, _lib.ptr(out), _lib.ptr(partial))
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        return dy, dy, None
+        return dy, dy, None, None
 
 
-def bias_residual_add(a, b, bias):
-    """a + b + bias[None, :, None, None] in one pass (ResBlock tail `skip(x) + out_conv(h)` with the conv biases deferred)."""
-    return _BiasResidualAdd.apply(a, b, bias)
+def _partial_buffer(N, HW, C, device):
+    return torch.empty(_lib.load().cg_groupnorm_nhwc_workspace_bytes(N, HW, C), device=device, dtype=torch.uint8)
+
+
+def bias_residual_add(a, b, bias, stats=False):
+    """a + b + bias[None, :, None, None] in one pass (ResBlock tail `skip(x) + out_conv(h)` with the conv biases deferred).
+
+    stats=True: the kernel also writes the chunk partials of its result for the GroupNorm that consumes it next; they ride on the
+    returned tensor as `._gn_partial` (see group_norm_nhwc(input_partial=...))."""
+    partial = _partial_buffer(a.shape[0], a.shape[2] * a.shape[3], a.shape[1], a.device) if stats else None
+    out = _BiasResidualAdd.apply(a, b, bias, partial)
+    if stats:
+        out._gn_partial = partial
+    return out
 
 
 def _resample2x(x, up, scale):
@@ -164,22 +185,30 @@ def _split_channels(cat, ca, cb):
 
 class _ConcatChannels(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, partial):
         a, b = _require_nhwc_half(a, "concat_channels"), _require_nhwc_half(b, "concat_channels")
         if a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
             raise ValueError("shape mismatch: %s vs %s" % (tuple(a.shape), tuple(b.shape)))
         N, ca, H, W = a.shape
         cb = b.shape[1]
         out = torch.empty((N, ca + cb, H, W), device=a.device, dtype=a.dtype, memory_format=torch.channels_last)
-        _lib.call("cg_concat2_nhwc", _lib.ptr(a), ca, _lib.ptr(b), cb, N * H * W, _lib.ptr(out), 0)
+        if partial is None:
+            _lib.call("cg_concat2_nhwc", _lib.ptr(a), ca, _lib.ptr(b), cb, N * H * W, _lib.ptr(out), 0)
+        else:
+            _lib.call("cg_concat2_stats_nhwc", _lib.ptr(a), ca, _lib.ptr(b), cb, N, H * W, _lib.ptr(out), _lib.ptr(partial))
         ctx.widths = (ca, cb)
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        return _split_channels(dy, *ctx.widths)  # two dense tensors in one pass (not strided views that every consumer re-copies)
+        return _split_channels(dy, *ctx.widths) + (None,)  # two dense tensors in one pass (not strided views that every consumer re-copies)
 
 
-def concat_channels(a, b):
-    """torch.cat([a, b], dim=1) on channels_last fp16 (the UNet's skip connections), with a one-pass split as its gradient."""
-    return _ConcatChannels.apply(a, b)
+def concat_channels(a, b, stats=False):
+    """torch.cat([a, b], dim=1) on channels_last fp16 (the UNet's skip connections), with a one-pass split as its gradient.
+    stats=True: also emits the next GroupNorm's chunk partials (`._gn_partial`, see bias_residual_add)."""
+    partial = _partial_buffer(a.shape[0], a.shape[2] * a.shape[3], a.shape[1] + b.shape[1], a.device) if stats else None
+    out = _ConcatChannels.apply(a, b, partial)
+    if stats:
+        out._gn_partial = partial
+    return out

@@ -193,10 +193,13 @@ int cg_dynamic_threshold(const float* x, int B, int64_t n, float q, float min_th
  * stats [N,G,2] (mean, rstd) and coef [2,N,C] (the folded per-channel affine a_c, b_c) are outputs kept for the backward.
  * pre_bias [C] fp32 or NULL: bias of the convolution that produced x, deferred into this op -- the normalised tensor is x + pre_bias_c
  * (folded into the per-group statistics and the per-channel affine; costs no memory pass).
+ * input_partial or NULL: per-chunk channel sums of x already produced by the kernel that wrote x (cg_bias_residual_add_stats_nhwc /
+ * cg_concat2_stats_nhwc, same N, HW, C): the statistics pass over x is skipped.
  * workspace: cg_groupnorm_nhwc_workspace_bytes(N,HW,C) bytes, 16-byte aligned. */
 size_t cg_groupnorm_nhwc_workspace_bytes(int N, int HW, int C);
 int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G, const float* gamma, const float* beta, const float* scale_shift,
-                          const float* pre_bias, float eps, int silu, int out_f32, void* y, float* stats, float* coef, void* workspace, void* stream);
+                          const float* pre_bias, const void* input_partial, float eps, int silu, int out_f32, void* y, float* stats, float* coef,
+                          void* workspace, void* stream);
 /* input gradient of the above (weights are frozen, models.py:67-71 / :120-127): dy [N,HW,C] fp16 (dy_f32 == 0) or fp32,
  * x / stats / coef as given to / produced by the forward -> dx [N,HW,C] fp16.  dres [N,HW,C] fp16 or NULL is added to dx: the
  * gradient that reaches x through its other consumer (the block's residual / skip path), saving autograd's separate accumulation pass. */
@@ -215,6 +218,11 @@ int cg_resample2x_nhwc(const void* x, int N, int H, int W, int C, int up, float 
  *   split != 0: the inverse -- a and b are WRITTEN from cat             (the concatenation's gradient)
  * a [rows,Ca], b [rows,Cb], cat [rows,Ca+Cb] fp16; Ca, Cb multiples of 8. */
 int cg_concat2_nhwc(void* a, int Ca, void* b, int Cb, int64_t rows, void* cat, int split, void* stream);
+/* The same two producers, additionally writing the chunk partials (sum, sum of squares per channel and row chunk, of the fp16 values
+ * they store) that a following cg_groupnorm_nhwc_fwd over [N,HW,C] accepts as input_partial.  partial: cg_groupnorm_nhwc_workspace_bytes
+ * (N,HW,C) bytes.  out / cat [N,HW,C] fp16 with C = Ca + Cb for the concatenation. */
+int cg_bias_residual_add_stats_nhwc(const void* a, const void* b, const float* bias, int N, int HW, int C, void* out, void* partial, void* stream);
+int cg_concat2_stats_nhwc(const void* a, int Ca, const void* b, int Cb, int N, int HW, void* cat, void* partial, void* stream);
 
 #ifdef __cplusplus
 }

@@ -141,6 +141,36 @@ def test_concat_channels_and_split_gradient(shape, cb):
     assert ga.is_contiguous(memory_format=torch.channels_last) and gb.is_contiguous(memory_format=torch.channels_last)
 
 
+@pytest.mark.parametrize("shape", [(1, 128, 64, 64), (2, 64, 9, 14), (1, 1024, 8, 8), (1, 256, 96, 128)])
+def test_producers_emit_the_next_groupnorm_statistics(shape):
+    """bias_residual_add / concat_channels with stats=True: same result as without, and a GroupNorm fed their `._gn_partial`
+    (no statistics pass of its own) equals the GroupNorm that reduces the tensor itself -- forward and backward."""
+    from clip_diffusion_b200 import unet_ops
+
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(C + W)
+    cl = torch.channels_last
+    a = torch.randn(shape, generator=g).half().cuda().contiguous(memory_format=cl)
+    b = (torch.randn(shape, generator=g) + 0.5).half().cuda().contiguous(memory_format=cl)
+    bias = torch.randn(C, generator=g).cuda()
+    gamma, beta = torch.rand(C, generator=g).cuda() + 0.5, torch.randn(C, generator=g).cuda()
+    for make, width in ((lambda st: unet_ops.bias_residual_add(a, b, bias, stats=st), C), (lambda st: unet_ops.concat_channels(a, b, stats=st), 2 * C)):
+        plain, withst = make(False), make(True)
+        assert torch.equal(plain, withst) and not hasattr(plain, "_gn_partial") and withst._gn_partial.is_cuda
+        gm, bt = (gamma, beta) if width == C else (torch.cat([gamma, gamma]), torch.cat([beta, beta]))
+        x0 = plain.detach().requires_grad_()
+        x1 = withst.detach().requires_grad_()
+        y0 = unet_ops.group_norm_nhwc(x0, gm, bt, 32, 1e-5, silu=True)
+        y1 = unet_ops.group_norm_nhwc(x1, gm, bt, 32, 1e-5, silu=True, input_partial=withst._gn_partial)
+        assert _rel(y1.float(), y0.float()) <= 1e-6, _rel(y1.float(), y0.float())
+        dy = torch.randn(y0.shape, generator=g).half().cuda()
+        (g0,) = torch.autograd.grad(y0, x0, dy)
+        (g1,) = torch.autograd.grad(y1, x1, dy)
+        assert _rel(g1.float(), g0.float()) <= 1e-6
+    with pytest.raises(ValueError):
+        unet_ops.group_norm_nhwc(a, gamma, beta, 32, 1e-5, input_partial=torch.empty(16, dtype=torch.uint8, device="cuda"))
+
+
 def test_resample2x_rejects_odd_sizes():
     from clip_diffusion_b200 import _lib, unet_ops
 
