@@ -1,20 +1,24 @@
-// Fused GroupNorm32 (+ scale-shift) (+ SiLU) forward / input-gradient for the NHWC fp16 activations of the replicated
-// guided-diffusion UNet (the UNet is built at clip_diffusion/models.py:87-131, its blocks are
-// restated in App. A.3: ResBlock = GN32 -> SiLU -> conv, GN32 -> *(1+scale)+shift -> SiLU -> conv; AttentionBlock = GN32 -> qkv).
+// NHWC fp16 kernels for everything BETWEEN the cuDNN convolutions of the replicated guided-diffusion UNet (the
+// UNet is built at clip_diffusion/models.py:87-131, its blocks are restated in App. A.3: ResBlock = GN32 -> SiLU -> conv,
+// GN32 -> *(1+scale)+shift -> SiLU -> conv, + skip; AttentionBlock = GN32 -> qkv; resblock_updown resamplers; skip concatenations).
 //
-// Why: after the CLIP side ran on tensor cores, a 512x512 guidance step spent ~25 of 60 ms in stock element-wise kernels
-// around cuDNN (NCHW<->NHWC transposes 10 ms, addcmul 7.6 ms, Welford/sum reductions 5 ms, SiLU fwd/bwd 2 ms ...;
-// profiles/r01_c2_step_kernel_table_*).  Keeping the trunk NHWC removes the transposes, and these kernels make every
-// normalisation 3 (forward) / 5 (backward) HBM passes over the activation instead of 10-14:
+// Why: after the CLIP side ran on tensor cores, a 512x512 guidance step spent ~25 of 60 ms in stock element-wise kernels around
+// cuDNN (NCHW<->NHWC transposes 10 ms, addcmul 7.6 ms, Welford/sum reductions 5 ms, SiLU 2 ms, conv-bias passes 2.9 ms ...;
+// profiles/r01_c2_step_kernel_table_*).  Keeping the trunk NHWC removes the transposes; these kernels make a normalisation
+// 2-3 (forward) / 5-6 (backward) HBM passes over the activation instead of 10-14:
 //
-//   forward : partial (per-channel sum / sum of squares per row chunk)  ->  finalize (mean, rstd per group in fp64, per-channel
-//             affine a_c, b_c with gamma/beta and the timestep scale-shift folded in)  ->  apply y = act(a_c*x + b_c)
+//   forward : partial (per-channel sum / sum of squares per row chunk; skipped when the producer of x already wrote them)
+//             -> finalize (mean, rstd per group in fp64; per-channel affine a_c, b_c with gamma/beta, the timestep scale-shift and the
+//             producing convolution's deferred bias folded in)  ->  apply y = act(a_c*x + b_c)
 //   backward: partial (per-channel sum dv and sum dv*x, dv = dy*silu'(a_c*x+b_c) recomputed)  ->  finalize (per-group B, C)
-//             ->  apply dx = a_c*dv + B_g*x + C_g
+//             ->  apply dx = a_c*dv + B_g*x + C_g (+ the gradient reaching x through the block's skip path)
+//   others  : bias + residual add, 2x average-pool / nearest-upsample (each the other's gradient), skip concat / split; the add and
+//             the concat can emit the next normalisation's partials while they stream their result out.
 //
-// All three are HBM-bound streaming kernels: 128-bit loads of 8 channels per thread, a thread keeps ONE channel octet for
-// its whole life (coefficients live in registers), rows are split into chunks so the grid is ~4 CTAs per SM for the large
-// levels, four independent loads in flight per thread.  No atomics: partials are reduced in a fixed order => deterministic.
+// All are HBM-bound streaming kernels: 128-bit accesses of 8 channels per thread, a thread keeps ONE channel octet for its
+// whole life (coefficients live in registers), rows are split into chunks (~8 CTAs per SM at the large levels), four independent
+// loads in flight per thread (volatile ld.global.nc -- see ldg_stream).  No atomics: partials are reduced in a fixed order =>
+// deterministic.  Every launch is a programmatic dependent launch (griddepcontrol), which also survives CUDA-graph capture.
 // Weights are frozen (models.py:120-127 only re-enables grads that never reach the sampler state) => no dgamma/dbeta.
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -223,19 +227,6 @@ __device__ __forceinline__ void block_sum2_f64(double& a, double& b, double* red
     a += red[2 * k];
     b += red[2 * k + 1];
   }
-}
-
-__device__ __forceinline__ double block_sum_f64(double v, double* red /*>=32*/) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) red[wid] = v;
-  __syncthreads();
-  const int nw = (blockDim.x + 31) >> 5;
-  double t = 0.0;
-  for (int k = 0; k < nw; ++k) t += red[k];
-  return t;
 }
 
 constexpr int kFinalizeThreads = 512;
