@@ -23,4 +23,7 @@ What is restated here, and what pins it
   against transformers' CLIPVisionModelWithProjection (quick_gelu) with mapped
   weights.
 * ``oracle.cond_fn``       -- restatement of the closure sample.py:134-238.
+* ``oracle.unet_norm``     -- the replicated UNet's normalisation blocks (guided-diffusion GroupNorm32 / scale-shift / SiLU, un-vendored:
+  **parity unpinned** against the package; built at clip_diffusion/models.py:87-131) and the folded algebra csrc/unet_norm.cu implements,
+  pinned against float64 autograd of the definition on the CPU.
 """

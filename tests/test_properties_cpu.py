@@ -61,3 +61,33 @@ def test_reference_in_place_equals_oracle_for_any_configuration(cfg):
     torch.manual_seed(seed)
     rec = draw_cutout_record(H, W, cs, no, ni, power, gray, noise="cpu")
     assert torch.equal(OC.make_cutouts(x, rec), ref)
+
+
+@pytest.mark.parametrize("shape,groups", [((2, 16, 5, 7), 4), ((1, 32, 6, 6), 32), ((3, 24, 4, 9), 2)])
+@pytest.mark.parametrize("silu", [False, True])
+@pytest.mark.parametrize("with_ss", [False, True])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_unet_norm_folded_algebra_matches_autograd_of_the_definition(shape, groups, silu, with_ss, with_bias):
+    """The formulas csrc/unet_norm.cu implements (oracle/unet_norm.folded_*: statistics of x + conv_bias from the per-channel sums
+    of x, one per-channel affine, closed-form input gradient with the skip-path gradient added) against float64 autograd of the
+    block arithmetic as guided-diffusion spells it (oracle/unet_norm.resblock_norm_reference)."""
+    import numpy as np
+
+    from oracle import unet_norm as U
+
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(n * 100 + c + (7 if silu else 0))
+    x = (torch.randn(shape, generator=g, dtype=torch.float64) * 1.3 + torch.randn(1, c, 1, 1, generator=g, dtype=torch.float64)).requires_grad_()
+    gamma = 1 + 0.3 * torch.randn(c, generator=g, dtype=torch.float64)
+    beta = 0.2 * torch.randn(c, generator=g, dtype=torch.float64)
+    ss = 0.4 * torch.randn(n, 2 * c, generator=g, dtype=torch.float64) if with_ss else None
+    cb = 1.5 * torch.randn(c, generator=g, dtype=torch.float64) if with_bias else None
+    dy = torch.randn(shape, generator=g, dtype=torch.float64)
+    dres = torch.randn(shape, generator=g, dtype=torch.float64)
+    y = U.resblock_norm_reference(x, gamma, beta, groups, 1e-5, ss, cb, silu)
+    (dx,) = torch.autograd.grad((y * dy).sum() + (x * dres).sum(), x)  # x also feeds the block's skip path
+    np_ = lambda t: None if t is None else t.detach().numpy()
+    y2 = U.folded_forward(np_(x), np_(gamma), np_(beta), groups, 1e-5, np_(ss), np_(cb), silu)
+    dx2 = U.folded_backward(np_(dy), np_(x), np_(gamma), np_(beta), groups, 1e-5, np_(ss), np_(cb), silu, np_(dres))
+    assert np.abs(y2 - np_(y)).max() <= 1e-10 * max(1.0, np.abs(np_(y)).max())
+    assert np.abs(dx2 - np_(dx)).max() <= 1e-9 * max(1.0, np.abs(np_(dx)).max())
