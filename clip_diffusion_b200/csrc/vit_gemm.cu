@@ -37,6 +37,7 @@ struct GemmArgs {
   long long ldo;
   const float* pos;
   int g2;
+  int wide;  // rows of out / aux are 32-byte aligned: the epilogue may use 256-bit global accesses
 };
 
 using namespace tc;
@@ -62,9 +63,72 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  In the epilogue a THREAD owns a row (tcgen05.ld 32x32b layout), so a warp
+// instruction touches 32 different rows: with 16-byte accesses every 32-byte sector is written in two half-sector transactions; with
+// 32-byte accesses each lane fills whole sectors and the number of LSU/L2 transactions halves (the bf16 epilogues were store-path
+// bound: 2 TB/s of DRAM traffic at 53 % of the tensor peak).  Needs 32-byte aligned rows: g.wide is set by the host when they are.
+__device__ __forceinline__ void st256(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]),
+               "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld256(const void* p, uint32_t* w) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p)
+               : "memory");
+}
+// 32 consecutive fp32 / bf16 values of one row
+__device__ __forceinline__ void store_f32x32(float* dst, const float* v, bool wide) {
+  if (wide) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st256(dst + 8 * j, reinterpret_cast<const uint32_t*>(v + 8 * j));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+}
+__device__ __forceinline__ void load_f32x32(const float* src, float* r, bool wide) {
+  if (wide) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ld256(src + 8 * j, reinterpret_cast<uint32_t*>(r + 8 * j));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 p = reinterpret_cast<const float4*>(src)[j];
+      r[4 * j] = p.x; r[4 * j + 1] = p.y; r[4 * j + 2] = p.z; r[4 * j + 3] = p.w;
+    }
+  }
+}
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v, bool wide) {
+  uint32_t w[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+  if (wide) {
+    st256(dst, w);
+    st256(dst + 16, w + 8);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(dst)[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  }
+}
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, uint32_t* w, bool wide) {
+  if (wide) {
+    ld256(src, w);
+    ld256(src + 16, w + 8);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(src) + j);
+      w[4 * j] = a.x; w[4 * j + 1] = a.y; w[4 * j + 2] = a.z; w[4 * j + 3] = a.w;
+    }
+  }
+}
+
 // one 32-column chunk of one output row
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, long long row, long long orow, int col, const uint32_t* acc_u) {
+  const bool wide = g.wide != 0;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc_u[j]);
@@ -77,56 +141,38 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, long long row,
     }
   }
   if (EPI == CG_EPI_BIAS_RESID_F32 || EPI == CG_EPI_F32 || EPI == CG_EPI_PATCH_POS_F32) {
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + orow * g.ldo + col);
+    float* o = reinterpret_cast<float*>(g.out) + orow * g.ldo + col;
     if (EPI == CG_EPI_PATCH_POS_F32) {
       const float4* p4 = reinterpret_cast<const float4*>(g.pos + (1 + row % g.g2) * (long long)g.N + col);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 p = __ldg(p4 + j);
-        o4[j] = make_float4(v[4 * j] + p.x, v[4 * j + 1] + p.y, v[4 * j + 2] + p.z, v[4 * j + 3] + p.w);
+        v[4 * j] += p.x; v[4 * j + 1] += p.y; v[4 * j + 2] += p.z; v[4 * j + 3] += p.w;
       }
     } else if (EPI == CG_EPI_BIAS_RESID_F32) {
-      const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.aux) + orow * g.ldo + col);
+      float r[32];
+      load_f32x32(reinterpret_cast<const float*>(g.aux) + orow * g.ldo + col, r, wide);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 p = r4[j];
-        o4[j] = make_float4(v[4 * j] + p.x, v[4 * j + 1] + p.y, v[4 * j + 2] + p.z, v[4 * j + 3] + p.w);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 32; ++j) v[j] += r[j];
     }
+    store_f32x32(o, v, wide);
   } else {
-    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + col);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + col;
     if (EPI == CG_EPI_BIAS_QGELU_BF16) {
-      uint4* a4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.aux) + orow * g.ldo + col);
+      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.aux) + orow * g.ldo + col, v, wide);  // pre-activation for the backward
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        a4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                           pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        // the backward differentiates QuickGELU at the bf16-rounded pre-activation it stored
-        v[j] = qgelu(v[j]);
-      }
+      for (int j = 0; j < 32; ++j) v[j] = qgelu(v[j]);
     } else if (EPI == CG_EPI_DQGELU_BF16) {
-      const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.aux) + orow * g.ldo + col);
+      uint32_t w[16];
+      load_bf16x32(reinterpret_cast<const __nv_bfloat16*>(g.aux) + orow * g.ldo + col, w, wide);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 a = __ldg(a4 + j);
-        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-          v[8 * j + 2 * k] *= qgelu_grad(__low2float(p));
-          v[8 * j + 2 * k + 1] *= qgelu_grad(__high2float(p));
-        }
+      for (int j = 0; j < 16; ++j) {
+        const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+        v[2 * j] *= qgelu_grad(__low2float(p));
+        v[2 * j + 1] *= qgelu_grad(__high2float(p));
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      o4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                         pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    store_bf16x32(o, v, wide);
   }
 }
 
@@ -597,6 +643,20 @@ extern "C" int cg_gemm_bf16_tn(const void* A, const void* B, int M, int N, int K
   CG_REQUIRE(!needs_bias || bias, "cg_gemm_bf16_tn: epilogue %d needs a bias", epilogue);
   CG_REQUIRE((epilogue != CG_EPI_BIAS_QGELU_BF16 && epilogue != CG_EPI_DQGELU_BF16 && epilogue != CG_EPI_BIAS_RESID_F32) || aux, "cg_gemm_bf16_tn: epilogue %d needs aux", epilogue);
   CG_REQUIRE(epilogue != CG_EPI_PATCH_POS_F32 || (pos && g2 > 0 && M % g2 == 0), "cg_gemm_bf16_tn: patch epilogue needs pos and g2 | M");
+  // 256-bit epilogue accesses: every row start of out (and aux) must be 32-byte aligned.  Element size: fp32 outputs 4, bf16 2;
+  // aux is fp32 for the residual epilogue, bf16 for the QuickGELU ones.  CG_GEMM_WIDE=0 forces the 128-bit path.
+  static int wide_env = -1;
+  if (wide_env < 0) {
+    const char* e = getenv("CG_GEMM_WIDE");
+    wide_env = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const bool out_f32 = epilogue == CG_EPI_BIAS_RESID_F32 || epilogue == CG_EPI_F32 || epilogue == CG_EPI_PATCH_POS_F32;
+  const long long row_bytes = (long long)ldo * (out_f32 ? 4 : 2);
+  const long long aux_row_bytes = (long long)ldo * (epilogue == CG_EPI_BIAS_RESID_F32 ? 4 : 2);
+  const int wide = (wide_env && epilogue != CG_EPI_PATCH_POS_F32 && ((uintptr_t)out & 31) == 0 && row_bytes % 32 == 0 &&
+                    (!aux || (((uintptr_t)aux & 31) == 0 && aux_row_bytes % 32 == 0)))
+                       ? 1
+                       : 0;
   const int bn = (N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, tb;
   int rc = make_tensor_map(&ta, A, M, K, lda, BM);
@@ -604,12 +664,12 @@ extern "C" int cg_gemm_bf16_tn(const void* A, const void* B, int M, int N, int K
   if (bn == 256 && M > 2 * BM && use_pair_kernel(M, N, K, epilogue)) {
     rc = make_tensor_map(&tb, B, N, K, ldb, BN2 / 2);
     if (rc) return rc;
-    GemmArgs gp = {M, N, K, bias, out, aux, (long long)ldo, pos, g2};
+    GemmArgs gp = {M, N, K, bias, out, aux, (long long)ldo, pos, g2, wide};
     return dispatch_pair(epilogue, ta, tb, gp, cg_stream(stream));
   }
   rc = make_tensor_map(&tb, B, N, K, ldb, bn);
   if (rc) return rc;
-  GemmArgs g = {M, N, K, bias, out, aux, (long long)ldo, pos, g2};
+  GemmArgs g = {M, N, K, bias, out, aux, (long long)ldo, pos, g2, wide};
   cudaStream_t s = cg_stream(stream);
   return bn == 256 ? dispatch<256>(epilogue, ta, tb, g, s) : dispatch<128>(epilogue, ta, tb, g, s);
 }
