@@ -83,6 +83,7 @@ _SIGNATURES = {
     "cg_dynamic_threshold_workspace_bytes": (C.c_size_t, [_I]),
     "cg_dynamic_threshold": (_I, [_P, _I, _L, _F, _F, _P, _P, _P, _P]),
     "cg_groupnorm_nhwc_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "cg_groupnorm_nhwc_geometry": (_I, [_I, _I, _I, C.POINTER(C.c_int)]),
     "cg_groupnorm_nhwc_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P]),
     "cg_bias_residual_add_stats_nhwc": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "cg_concat2_stats_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P]),

@@ -708,6 +708,18 @@ extern "C" size_t cg_groupnorm_nhwc_workspace_bytes(int N, int HW, int C) {
   return (size_t)N * g.chunks * C * sizeof(float2) + (size_t)2 * N * C * sizeof(float);
 }
 
+extern "C" int cg_groupnorm_nhwc_geometry(int N, int HW, int C, int* out5) {
+  if (int rc = check_shape(N, HW, C, 1)) return rc;
+  CG_REQUIRE(out5, "groupnorm_nhwc_geometry: null pointer");
+  const Geo g = geometry(N, HW, C);
+  out5[0] = g.cvecs;
+  out5[1] = g.rows_per_iter;
+  out5[2] = g.threads;
+  out5[3] = g.chunks;
+  out5[4] = g.rows_per_chunk;
+  return 0;
+}
+
 extern "C" int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G, const float* gamma, const float* beta, const float* scale_shift,
                                      const float* pre_bias, const void* input_partial, float eps, int silu, int out_f32, void* y, float* stats,
                                      float* coef, void* workspace, void* stream) {

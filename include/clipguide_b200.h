@@ -197,6 +197,10 @@ int cg_dynamic_threshold(const float* x, int B, int64_t n, float q, float min_th
  * cg_concat2_stats_nhwc, same N, HW, C): the statistics pass over x is skipped.
  * workspace: cg_groupnorm_nhwc_workspace_bytes(N,HW,C) bytes, 16-byte aligned. */
 size_t cg_groupnorm_nhwc_workspace_bytes(int N, int HW, int C);
+/* Host-only: the launch geometry the normalisation kernels (and the *_stats producers) use for a [N,HW,C] tensor --
+ * out5 = {channel octets per row, rows per CTA iteration, threads per CTA, row chunks per sample (gridDim.x), rows per chunk}.
+ * Exposed so that the chunking invariants can be tested without a GPU. */
+int cg_groupnorm_nhwc_geometry(int N, int HW, int C, int* out5);
 int cg_groupnorm_nhwc_fwd(const void* x, int N, int HW, int C, int G, const float* gamma, const float* beta, const float* scale_shift,
                           const float* pre_bias, const void* input_partial, float eps, int silu, int out_f32, void* y, float* stats, float* coef,
                           void* workspace, void* stream);

@@ -126,6 +126,29 @@ def test_groupnorm_workspace_query_is_host_only_and_sane():
     assert lib.cg_groupnorm_nhwc_workspace_bytes(2, 4096, 256) % 16 == 0
 
 
+def test_groupnorm_chunk_geometry_covers_every_row_once():
+    """Launch geometry of csrc/unet_norm.cu (host-only query): threads = octets x row lanes <= 256, the row chunks tile [0, HW)
+    without gap or overlap, chunks are whole unrolled iterations when the map is large, and the workspace holds all partials."""
+    import ctypes as C
+
+    from clip_diffusion_b200 import _lib
+
+    lib = _lib.load()
+    out = (C.c_int * 5)()
+    shapes = [(1, 512 * 512, 128), (1, 512 * 512, 256), (1, 768 * 768, 128), (1, 256 * 256, 512), (1, 64, 1024), (1, 256, 2048), (2, 63, 32),
+              (3, 33 * 31, 256), (1, 24 * 40, 384), (1, 1, 8), (7, 4096, 1536), (1, 96 * 96, 768), (64, 16, 64)]
+    for n, hw, c in shapes:
+        assert lib.cg_groupnorm_nhwc_geometry(n, hw, c, out) == 0
+        cvecs, rpi, threads, chunks, rpc = list(out)
+        assert cvecs == c // 8 and rpi >= 1 and threads == cvecs * rpi and threads <= 256
+        assert chunks >= 1 and rpc >= 1 and chunks * rpc >= hw and (chunks - 1) * rpc < hw  # exact tiling of the rows
+        if hw >= 64 * rpi * 4:
+            assert rpc % (rpi * 4) == 0  # whole unrolled iterations per chunk
+            assert chunks * n <= 8 * 148 + n  # ~8 CTAs per SM
+        assert lib.cg_groupnorm_nhwc_workspace_bytes(n, hw, c) >= n * chunks * c * 8 + 2 * n * c * 4
+    assert lib.cg_groupnorm_nhwc_geometry(1, 64, 12, out) != 0 and lib.cg_groupnorm_nhwc_geometry(1, 64, 4096, out) != 0
+
+
 def test_group_norm32_stock_path_spells_the_resblock_arithmetic():
     """GroupNorm32(x, scale_shift, silu) on the CPU / fp32 path == silu(GN(x) * (1 + scale) + shift) (guided-diffusion ResBlock)."""
     from torch.nn import functional as Fn
