@@ -100,7 +100,11 @@ class GroupNorm32(nn.GroupNorm):
     nhwc = False
 
     def forward(self, x, scale_shift=None, silu=False, out_dtype=None, pre_bias=None, passthrough=False, input_partial=None):
-        if self.nhwc and x.is_cuda and x.dtype == torch.float16:
+        if self.nhwc and not (x.is_cuda and x.dtype == torch.float16):
+            # a model built for the NHWC kernels never drops to the stock ops behind the caller's back
+            raise RuntimeError("GroupNorm32(nhwc=True) needs fp16 CUDA activations (got %s on %s); build the model with "
+                               "create_unet(channels_last=False) for the stock-PyTorch path" % (x.dtype, x.device))
+        if self.nhwc:
             from clip_diffusion_b200.unet_ops import group_norm_nhwc
 
             if input_partial is None:  # statistics partials written by the op that produced x (bias_residual_add / concat_channels)
@@ -352,6 +356,8 @@ def create_unet(image_size=512, seed=2, device="cuda", use_fp16=True, config=Non
     model = model.to(device).eval().requires_grad_(False)
     if channels_last is None:
         channels_last = use_fp16 and torch.device(device).type == "cuda"
+    if channels_last and not (use_fp16 and torch.device(device).type == "cuda"):
+        raise ValueError("channels_last=True selects the sm_100a NHWC kernels: it needs device='cuda' and use_fp16=True (there is no CPU / fp32 variant)")
     if channels_last:
         # cuDNN's tensor-core convolutions are NHWC: keep the whole trunk NHWC instead of transposing around every conv, with the
         # normalisation / activation work between the convs in fused NHWC kernels (unet_ops.group_norm_nhwc)

@@ -149,6 +149,18 @@ def test_groupnorm_chunk_geometry_covers_every_row_once():
     assert lib.cg_groupnorm_nhwc_geometry(1, 64, 12, out) != 0 and lib.cg_groupnorm_nhwc_geometry(1, 64, 4096, out) != 0
 
 
+def test_nhwc_unet_is_never_built_or_run_without_its_kernels():
+    """channels_last=True means the sm_100a kernels: refused on the CPU / in fp32, and an NHWC GroupNorm32 fed anything else raises."""
+    from clip_diffusion_b200.unet import GroupNorm32, create_unet
+
+    with pytest.raises(ValueError):
+        create_unet(32, device="cpu", use_fp16=False, channels_last=True)
+    gn = GroupNorm32(4, 16)
+    gn.nhwc = True
+    with pytest.raises(RuntimeError):
+        gn(torch.zeros(1, 16, 4, 4))
+
+
 def test_group_norm32_stock_path_spells_the_resblock_arithmetic():
     """GroupNorm32(x, scale_shift, silu) on the CPU / fp32 path == silu(GN(x) * (1 + scale) + shift) (guided-diffusion ResBlock)."""
     from torch.nn import functional as Fn
