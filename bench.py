@@ -5,12 +5,13 @@
 
 A "step" is ONE full CLIP-guided DDIM sampling step on synthetic inputs: the sampler's no-grad UNet forward, the
 guidance function (UNet forward with grad -> fused cutouts -> CLIP ViT fwd -> spherical loss+grad -> ViT dgrad ->
-cutout backward -> TV -> all-reduce -> UNet VJP -> RMS clamp) and the DDIM update.  Default workload = BASELINE.json
-configs[1]: 512x512 uncond guided-diffusion UNet (fp16, random init) + ViT-B/16, 16 overview + 16 inner cutouts,
-DDIM-250 schedule.  `value` is cutouts/s = steps/s x cutouts per step (steps/s is reported beside it as `steps_per_s`): SURVEY
-section 7 -- cutouts/s is the quantity that scales with GPUs, steps/s is bounded by the replicated UNet.  For N > 1 the cutout
-batch of every step is sharded across ranks (one NCCL all-reduce of the [3,512,512] fp32 image gradient per step, UNet
-replicated); --scaling weak (default) keeps the workload's cutouts PER RANK (N x cutouts per step), --scaling strong splits them.
+cutout backward -> TV -> all-reduce -> UNet VJP -> RMS clamp) and the DDIM update.  Default workload = north_star's
+Target: 512x512 uncond guided-diffusion UNet (fp16, random init) + ViT-L/14, 32 overview + 32 inner cutouts, DDIM-250
+schedule (`--workload c2` = BASELINE.json configs[1]).  `value` is cutouts/s = steps/s x cutouts per step (steps/s is
+reported beside it as `steps_per_s`).  For N > 1 the cutout batch of every step is sharded across ranks (one NCCL all-reduce
+of the [3,512,512] fp32 image gradient per step, UNet replicated); --scaling strong (default, configs[2] / north_star (4))
+splits the workload's 64 cutouts over the ranks -- the SAME job on more GPUs; --scaling weak keeps the workload's cutouts PER
+RANK (N x cutouts per step).  The strong-scaling line also carries the weak number as the secondary field `weak`.
 
 --impl reference times the CPU restatement of the reference path (oracle/, fp32, all host threads) on the same
 workload; see cpu_baseline in the JSON line.
@@ -49,16 +50,16 @@ def parse_args():
     p.add_argument("--steps", type=int, default=8)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                   help="N>1: weak = every rank keeps the workload's cutouts (N x cutouts per step, value in cutouts/s scales); "
-                        "strong = the workload's cutouts are split over the ranks")
+    p.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
+    p.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                   help="N>1: strong (default) = the workload's cutouts are split over the ranks (same job, more GPUs); "
+                        "weak = every rank keeps the workload's cutouts (N x cutouts per step)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graphs", action="store_true", help="do not capture the replicated UNet forward/backward into CUDA graphs")
     p.add_argument("--two-forwards", action="store_true", help="evaluate the UNet separately for the sampler and for cond_fn like the reference does")
     p.add_argument("--unet-layout", default="nhwc", choices=["nhwc", "nchw"],
                    help="nhwc (default): channels_last trunk + fused GroupNorm/scale-shift/SiLU kernels (csrc/unet_norm.cu); nchw: stock torch ops")
-    p.add_argument("--cpu-budget-s", type=float, default=240.0)
+    p.add_argument("--cpu-budget-s", type=float, default=150.0)
     return p.parse_args()
 
 
@@ -201,6 +202,16 @@ def build_cpu_reference(wl, seed=0, world=1, scaling="weak"):
     return step, x, ddim, (n_over + n_inner) * batches * len(names)
 
 
+def workload_config(wl, world, scaling):
+    """The `config` object of the JSON line: the WORKLOAD only, identical in both arms (b200 and --impl reference); everything
+    about how this implementation runs it goes to `impl_details`."""
+    size, names, _, _, batches, ddim, desc = WORKLOADS[wl]
+    n_over, n_inner = scaled_cuts(wl, world, scaling)
+    return {"workload": desc, "image": "%dx%d" % (size, size), "clip_models": list(names), "overview_cuts": n_over, "inner_cuts": n_inner,
+            "cutout_batches": batches, "cutouts_per_step": (n_over + n_inner) * batches * len(names), "ddim_steps": ddim, "eta": 0.8,
+            "dynamic_thresholding": 0.995, "n_gpus": world, "scaling": scaling if world > 1 else "n/a (1 GPU)"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -223,12 +234,66 @@ def run_reference(args, rank):
     line = {
         "impl": "reference", "metric": METRIC % (WORKLOADS[wl][0], WORKLOADS[wl][0]), "value": cuts * val, "unit": "cutouts/s", "n_gpus": args.gpus, "steps": k,
         "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[wl][6], "cutouts_per_step": cuts},
+        "config": workload_config(wl, args.gpus, args.scaling),
         "cpu_baseline": {"value": cuts * val, "unit": "cutouts/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": cuts * val, "unit": "cutouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_per_s": val,
     }
     print(json.dumps(line), flush=True)
+
+
+PROFILED = ("cg_gemm_bf16_tn", "cg_attention_fwd", "cg_attention_bwd", "cg_cutouts_fwd", "cg_cutouts_bwd", "cg_layernorm_fwd", "cg_layernorm_bwd",
+            "cg_tv_loss_fwd_bwd", "cg_range_loss_fwd_bwd", "cg_image_losses_fwd_bwd", "cg_spherical_loss_fwd_bwd")
+
+
+def kernel_rooflines(prof, step_ms, tf_peak, hbm_peak, peak_src, traffic):
+    """Per-kernel-family rooflines from the profiled pass: algorithmic work of every launch of the timed
+    region / sum of their CUDA-event durations on the launching stream."""
+    fam = {}
+
+    def add(key, work, ms):
+        f = fam.setdefault(key, [0.0, 0.0, 0])
+        f[0] += work
+        f[1] += ms
+        f[2] += 1
+
+    for name, a, e0, e1 in prof:
+        ms = e0.elapsed_time(e1)
+        if name == "cg_gemm_bf16_tn":
+            add("gemm", 2.0 * a[2] * a[3] * a[4], ms)
+        elif name == "cg_attention_fwd":  # (qkv, Nimg, T, heads, ...): QK^T + PV
+            add("attn_fwd", 4.0 * a[1] * a[3] * a[2] * a[2] * 64, ms)
+        elif name == "cg_attention_bwd":  # (qkv, ctx, dctx, lse, Nimg, T, heads, ...): dV, dP, dQ, dK (recomputing S is not counted)
+            add("attn_bwd", 8.0 * a[4] * a[6] * a[5] * a[5] * 64, ms)
+        elif name == "cg_cutouts_fwd":    # (x, H, W, cuts, n, cs, aug, noise, out, fmt, patch, kpad, ws): read the image once, write bf16 patches
+            g2 = (a[5] // a[10]) ** 2 if a[10] else 0
+            add("cutouts_fwd", 12.0 * a[1] * a[2] + (a[4] * g2 * a[11] * 2.0 if a[10] else a[4] * 3.0 * a[5] * a[5] * 4), ms)
+        elif name == "cg_cutouts_bwd":    # (dout, H, W, n, cs, fmt, patch, kpad, ...): read fp32 patch gradients, write the image gradient
+            g2 = (a[4] // a[6]) ** 2 if a[6] else 0
+            add("cutouts_bwd", 12.0 * a[1] * a[2] + (a[3] * g2 * a[7] * 4.0 if a[6] else a[3] * 3.0 * a[4] * a[4] * 4), ms)
+        elif name == "cg_layernorm_fwd":  # (x, g, b, M, D, ...): fp32 in, bf16 out
+            add("layernorm_fwd", 6.0 * a[3] * a[4], ms)
+        elif name == "cg_layernorm_bwd":  # reads dy, x, dx (fp32), writes dx (fp32) + bf16 copy
+            add("layernorm_bwd", 18.0 * a[5] * a[6], ms)
+        elif name in ("cg_tv_loss_fwd_bwd", "cg_range_loss_fwd_bwd", "cg_image_losses_fwd_bwd"):  # (x, B, C, H, W, ...): read + write the image
+            add("image_losses", 8.0 * a[1] * a[2] * a[3] * a[4], ms)
+    out = {}
+    steps_in_prof = max(1, sum(1 for n, *_ in prof if n in ("cg_tv_loss_fwd_bwd", "cg_image_losses_fwd_bwd")))
+    for key, (work, ms, cnt) in fam.items():
+        if ms <= 0:
+            continue
+        tensor = key in ("gemm", "attn_fwd", "attn_bwd")
+        achieved = work / (ms / 1e3) / (1e12 if tensor else 1e9)
+        peak = tf_peak if tensor else hbm_peak
+        out[key] = {"bound": "tensor" if tensor else "hbm", "achieved": achieved, "peak": peak, "unit": "TFLOP/s" if tensor else "GB/s",
+                    "frac": achieved / peak, "launches": cnt, "ms_per_step": ms / steps_in_prof,
+                    "share_of_step": (ms / steps_in_prof) / step_ms if step_ms > 0 else None,
+                    ("algorithmic_flops_per_launch" if tensor else "algorithmic_bytes_per_launch"): work / cnt}
+    g = out.get("gemm", {"achieved": 0.0, "frac": 0.0, "launches": 0, "share_of_step": None})
+    roof = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM/TMA, all ViT GEMMs)", "achieved": g["achieved"], "peak": tf_peak, "unit": "TFLOP/s",
+            "frac": g["frac"], "traffic": traffic, "algorithmic_flops_per_launch": g.get("algorithmic_flops_per_launch"), "peak_source": peak_src,
+            "launches": g["launches"], "share_of_step": g["share_of_step"]}
+    return roof, out
 
 
 def main():
@@ -242,7 +307,7 @@ def main():
 
     import torch.distributed as dist
 
-    from clip_diffusion_b200 import _lib, vit_ops
+    from clip_diffusion_b200 import _lib
     from clip_diffusion_b200.diffusion import SpacedDiffusion
     from clip_diffusion_b200.models import load_clip_models
     from clip_diffusion_b200.sample import GuidanceStep, make_denoised_function
@@ -258,8 +323,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     size, names, _, _, batches, ddim, desc = WORKLOADS[args.workload]
-    n_over, n_inner = scaled_cuts(args.workload, world, args.scaling)
-    cfg = make_cfg(n_over, n_inner, batches)
     set_seed(1234)
     clip_only = args.workload == "clip-only"
     unet = None if clip_only else create_unet(size if size in (256, 512) else 512, seed=2, device=dev, use_fp16=True, channels_last=args.unet_layout == "nhwc")
@@ -270,32 +333,19 @@ def main():
         # (profiles/r01_*): capture its forward and backward once into CUDA graphs (static shapes, batch 1).
         unet = graph_unet(unet, size, size, dev)
         unet_graphed = True
-    clip_models = load_clip_models(names, dev)
+    clip_models = load_clip_models(names, dev, allow_random_init=True)
     g = torch.Generator().manual_seed(0)
     text = {n: {"embeddings": torch.randn(1, m.visual.output_dim, generator=g).to(dev), "weights": torch.tensor(1.0, device=dev)} for n, m in clip_models.items()}
     predictors = None
     if args.workload == "c4":
         from clip_diffusion_b200.models import load_aesthetic_predictors
 
-        cfg.aesthetic_scale = 500
         predictors = load_aesthetic_predictors(names, dev)
-    guidance = GuidanceStep(diffusion, unet, clip_models, text, aesthetic_predictors=predictors, config=cfg, rank=rank, world_size=world,
-                            range_scale=150.0 if args.workload == "c3" else 0.0)
     denoised_fn = make_denoised_function(0.995)  # reference defaults: dynamic thresholding 0.995, eta 0.8 (sample.py:66-71)
-    cuts_per_step = (n_over + n_inner) * batches * len(names)
     x_host = torch.randn(1, 3, size, size, generator=g).pin_memory()
     out_host = torch.empty(2, 3, size, size).pin_memory()
     x_dev = x_host.to(dev)
     x_in_fixed = torch.tanh(x_dev).contiguous()
-
-    def step(x, i):
-        if clip_only:
-            gbuf = torch.zeros(3, size, size, device=dev)
-            guidance.clip_guidance_grad(x_in_fixed, 1000 - (int(diffusion.timestep_map[i]) + 1), gbuf)
-            if world > 1:
-                dist.all_reduce(gbuf)
-            return {"sample": x, "pred_xstart": gbuf.unsqueeze(0)}
-        return guidance.ddim_step(x, i, eta=0.8, denoised_fn=denoised_fn, reuse_forward=not args.two_forwards)
 
     def barrier():
         if world > 1:
@@ -309,60 +359,95 @@ def main():
             return float(t.item())
         return ms
 
-    W, K = max(args.warmup, 3), args.steps
-    i = ddim - 1
-    x = x_dev
     def next_i(i):  # walk the DDIM schedule downwards, wrapping so that any --steps/--warmup works
         return i - 1 if i > 0 else ddim - 1
 
-    for _ in range(W):
-        x = step(x, i)["sample"]
-        i = next_i(i)
-    # ---- timed region 1: inputs resident in HBM -------------------------------------------------
-    barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
-    vit_ops.PROFILE = []
-    k0 = _lib.kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    use_range = os.environ.get("CG_BENCH_PROFILER_RANGE") == "1"  # ncu --profile-from-start off: profile the timed region only
-    if use_range:
-        torch.cuda.profiler.start()
-    wall0 = time.time()
-    e0.record()
-    for _ in range(K):
-        x = step(x, i)["sample"]
-        i = next_i(i)
-    e1.record()
-    barrier()
-    if use_range:
-        torch.cuda.profiler.stop()
-    wall1 = time.time()
-    ms = tmax(e0.elapsed_time(e1))
-    launches = _lib.kernel_launches - k0
-    if unet_graphed:  # our GroupNorm / resample / concat kernels replayed inside the UNet's CUDA graphs (one forward + one backward per step)
-        launches += K * unet.own_kernels_per_replay
-    prof, vit_ops.PROFILE = vit_ops.PROFILE, None
-    gemm_ms = sum(a.elapsed_time(b) for _, a, b in prof)
-    gemm_flops = sum(f for f, _, _ in prof)
-    clk = clocks.summary(wall0, wall1) if clocks else None
-    # ---- timed region 2: end to end through host buffers ------------------------------------------
-    barrier()
-    e0.record()
-    for _ in range(K):
-        xd = x_host.to(dev, non_blocking=True)
-        out = step(xd, i)
-        out_host[0].copy_(out["sample"][0], non_blocking=True)
-        out_host[1].copy_(out["pred_xstart"][0].float(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller consumes the step result (PNG every step, sample.py:290-295)
-        i = next_i(i)
-    e1.record()
-    barrier()
-    ms_e2e = tmax(e0.elapsed_time(e1))
+    W, K = max(args.warmup, 3), args.steps
+
+    def measure(scaling, profile):
+        """W warm-up steps, then K timed steps with the state resident in HBM, K timed steps end to end through pinned host
+        buffers and (profile=True) K more steps with CUDA events around every C-ABI call for the kernel rooflines."""
+        n_over, n_inner = scaled_cuts(args.workload, world, scaling)
+        cfg = make_cfg(n_over, n_inner, batches)
+        if args.workload == "c4":
+            cfg.aesthetic_scale = 500
+        guidance = GuidanceStep(diffusion, unet, clip_models, text, aesthetic_predictors=predictors, config=cfg, rank=rank, world_size=world,
+                                range_scale=150.0 if args.workload == "c3" else 0.0)
+
+        def step(x, i):
+            if clip_only:
+                gbuf = torch.zeros(3, size, size, device=dev)
+                guidance.clip_guidance_grad(x_in_fixed, 1000 - (int(diffusion.timestep_map[i]) + 1), gbuf)
+                if world > 1:
+                    dist.all_reduce(gbuf)
+                return {"sample": x, "pred_xstart": gbuf.unsqueeze(0)}
+            return guidance.ddim_step(x, i, eta=0.8, denoised_fn=denoised_fn, reuse_forward=not args.two_forwards)
+
+        i = ddim - 1
+        x = x_dev
+        for _ in range(W):
+            x = step(x, i)["sample"]
+            i = next_i(i)
+        res = {"cuts_per_step": (n_over + n_inner) * batches * len(names), "n_over": n_over, "n_inner": n_inner}
+        # ---- timed region 1: inputs resident in HBM -------------------------------------------------
+        barrier()
+        clocks = ClockSampler(local_rank) if (rank == 0 and profile) else None
+        k0 = _lib.kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        use_range = profile and os.environ.get("CG_BENCH_PROFILER_RANGE") == "1"  # ncu --profile-from-start off: profile the timed region only
+        if use_range:
+            torch.cuda.profiler.start()
+        wall0 = time.time()
+        e0.record()
+        for _ in range(K):
+            x = step(x, i)["sample"]
+            i = next_i(i)
+        e1.record()
+        barrier()
+        if use_range:
+            torch.cuda.profiler.stop()
+        wall1 = time.time()
+        res["ms"] = tmax(e0.elapsed_time(e1))
+        res["launches"] = _lib.kernel_launches - k0
+        if unet_graphed:  # our GroupNorm / resample / concat kernels replayed inside the UNet's CUDA graphs (one forward + one backward per step)
+            res["launches"] += K * unet.own_kernels_per_replay
+        res["clocks"] = clocks.summary(wall0, wall1) if clocks else None
+        if not profile:
+            return res
+        # ---- timed region 2: end to end through host buffers ------------------------------------------
+        barrier()
+        e0.record()
+        for _ in range(K):
+            xd = x_host.to(dev, non_blocking=True)
+            out = step(xd, i)
+            out_host[0].copy_(out["sample"][0], non_blocking=True)
+            out_host[1].copy_(out["pred_xstart"][0].float(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller consumes the step result (PNG every step, sample.py:290-295)
+            i = next_i(i)
+        e1.record()
+        barrier()
+        res["ms_e2e"] = tmax(e0.elapsed_time(e1))
+        # ---- timed region 3: the same K steps with CUDA events around every C-ABI call (kernel rooflines; not part of `value`) ----
+        barrier()
+        _lib.PROFILE, _lib.PROFILE_NAMES = [], PROFILED
+        e0.record()
+        for _ in range(K):
+            x = step(x, i)["sample"]
+            i = next_i(i)
+        e1.record()
+        barrier()
+        res["prof"], _lib.PROFILE = _lib.PROFILE, None
+        res["ms_prof"] = e0.elapsed_time(e1)
+        return res
+
+    main_res = measure(args.scaling, profile=True)
+    weak_res = measure("weak", profile=False) if (world > 1 and args.scaling == "strong") else None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    ms, ms_e2e, cuts_per_step = main_res["ms"], main_res["ms_e2e"], main_res["cuts_per_step"]
     tf_peak, hbm_peak, peak_src = measured_peaks()
     traffic = None  # dram bytes per GEMM launch from the committed ncu capture of this same command (profiles/)
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic_%s.json" % args.workload)
@@ -371,22 +456,32 @@ def main():
             traffic = json.load(f).get("avg_dram_bytes_per_launch")
     value = K / (ms / 1e3)
     e2e = K / (ms_e2e / 1e3)
-    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    roof, fams = kernel_rooflines(main_res["prof"], main_res["ms_prof"] / K, tf_peak, hbm_peak, peak_src, traffic)
+    n_cut = main_res["n_over"] + main_res["n_inner"]
     line = {
         "metric": METRIC % (size, size), "value": cuts_per_step * value, "unit": "cutouts/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": desc, "cutouts_per_step": cuts_per_step, "cutouts_per_rank": -(-cuts_per_step // world), "unet_cuda_graphs": unet_graphed, "unet": "fp16, replicated, %s; %s" % ("channels_last cuDNN convs + fused NHWC GroupNorm/scale-shift/SiLU kernels" if args.unet_layout == "nhwc" else "NCHW stock PyTorch", "two forwards per step (sampler + cond_fn) like the reference" if args.two_forwards else "one grad-enabled forward shared by sampler and cond_fn (identical results)"),
-                   "clip": "bf16 operands / fp32 accumulate + fp32 residual stream, random init", "parallelism": "%d cutouts per (model, step) sharded over %d rank(s) = %d per rank, 1 all-reduce of the image gradient per step" % (n_over + n_inner, world, -(-(n_over + n_inner) // world)),
-                   "l2": "working set (1.1 GB UNet + ViT weights + activations) far exceeds the 126 MB L2; no flush"},
+        "config": workload_config(args.workload, world, args.scaling),
+        "impl_details": {"unet_cuda_graphs": unet_graphed, "unet": "fp16, replicated, %s; %s" % ("channels_last cuDNN convs + fused NHWC GroupNorm/scale-shift/SiLU kernels" if args.unet_layout == "nhwc" else "NCHW stock PyTorch", "two forwards per step (sampler + cond_fn) like the reference" if args.two_forwards else "one grad-enabled forward shared by sampler and cond_fn (identical results)"),
+                         "clip": "bf16 operands / fp32 accumulate + fp32 residual stream, random init",
+                         "parallelism": "%d cutouts per (model, step) sharded over %d rank(s) = %d per rank, 1 all-reduce of the image gradient per step" % (n_cut, world, -(-n_cut // world)),
+                         "cutouts_per_rank": -(-cuts_per_step // world),
+                         "l2": "working set (1.1 GB UNet + ViT weights + activations) far exceeds the 126 MB L2; no flush"},
         "steps_per_s": value,
         "e2e": {"value": cuts_per_step * e2e, "unit": "cutouts/s", "steps_per_s": e2e, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
-        "gpu_launches": launches,
-        "clocks": clk,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05/TMEM/TMA, all ViT GEMMs)", "achieved": achieved, "peak": tf_peak,
-                     "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
-                     "algorithmic_flops_per_launch": gemm_flops / max(len(prof), 1), "peak_source": peak_src, "launches": len(prof),
-                     "share_of_step": gemm_ms / ms if ms > 0 else None},
+        "gpu_launches": main_res["launches"],
+        "clocks": main_res["clocks"],
+        "roofline": roof,
     }
+    for key, label in (("attn_fwd", "roofline_attention_fwd"), ("attn_bwd", "roofline_attention_bwd"), ("cutouts_fwd", "roofline_cutouts_fwd"),
+                       ("cutouts_bwd", "roofline_cutouts_bwd"), ("layernorm_fwd", "roofline_layernorm_fwd"), ("layernorm_bwd", "roofline_layernorm_bwd"),
+                       ("image_losses", "roofline_image_losses")):
+        if key in fams:
+            line[label] = fams[key]
+    if weak_res is not None:
+        wv = K / (weak_res["ms"] / 1e3)
+        line["weak"] = {"value": weak_res["cuts_per_step"] * wv, "unit": "cutouts/s", "steps_per_s": wv, "ms_per_step": weak_res["ms"] / K,
+                        "cutouts_per_step": weak_res["cuts_per_step"], "note": "secondary: every rank keeps the workload's cutouts (N x cutouts per step)"}
     if unet is not None and args.unet_layout == "nhwc":
         line["roofline_unet_norm"] = unet_norm_roofline(dev, hbm_peak)
     if world == 1 and not args.no_cpu_baseline and not clip_only:

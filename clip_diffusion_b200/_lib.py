@@ -150,13 +150,26 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# bench.py sets this to a list to time C-ABI calls with CUDA events on the launching stream: entries are
+# (entry point name, args, start_event, end_event).  PROFILE_NAMES restricts it to the entry points of interest.
+PROFILE = None
+PROFILE_NAMES = ()
+
+
 def call(name, *args):
     """Call an int-returning entry point on the current stream (appended as last argument)."""
     global launch_count, kernel_launches
     lib = load()
     if name in lib._cg_missing:
         raise ClipGuideError("%s is not exported by %s: rebuild the library (stale build)" % (name, LIB_PATH))
+    prof = PROFILE is not None and name in PROFILE_NAMES
+    if prof:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = getattr(lib, name)(*args, stream_ptr())
+    if prof:
+        ev1.record()
+        PROFILE.append((name, args, ev0, ev1))
     launch_count += 1
     kernel_launches += _KERNELS_PER_CALL.get(name, 1)
     check(rc, name)

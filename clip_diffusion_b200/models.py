@@ -121,6 +121,7 @@ class VisionTransformerB200:
             blk["b_proj"] = _f32(sd[p + "mlp.c_proj.bias"], dev)
             self.blocks.append(blk)
         self._ws = {}  # persistent activation workspaces per batch size (stable addresses => TMA descriptor cache hits)
+        self._generation = 0  # bumped by every forward: the saved activations live in the shared workspace, not in an autograd ctx
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, n):
@@ -177,17 +178,31 @@ class VisionTransformerB200:
         emb = torch.empty(n, E, device=self.device, dtype=torch.float32)
         C("cg_vit_proj_fwd", P(ws["y"]), P(self.proj), n, D, E, P(emb))
         self._last_n = n
+        self._generation += 1
+        ws["generation"] = self._generation
         return emb
 
     # ------------------------------------------------------------------ backward (input gradient only)
-    def backward_patches(self, demb):
-        """demb [N, E] fp32 -> d(patches) [N, g*g, Kpad] fp32, for the activations of the latest forward."""
+    def backward_patches(self, demb, generation=None):
+        """demb [N, E] fp32 -> d(patches) [N, g*g, Kpad] fp32, for the activations of the latest forward.  The saved activations
+        live in the tower's per-batch-size workspace, which the next forward of the same size overwrites: ``generation`` (the
+        value of ``self._generation`` right after the forward this gradient belongs to) makes a stale backward an error instead
+        of a silently wrong gradient."""
         n = demb.shape[0]
-        if n != getattr(self, "_last_n", None):
+        ws = self._ws.get(n)
+        if ws is None or "generation" not in ws:
             raise RuntimeError("backward_patches must follow forward_patches with the same batch size")
+        if generation is None:
+            if n != getattr(self, "_last_n", None):
+                raise RuntimeError("backward_patches must follow forward_patches with the same batch size")
+        elif ws["generation"] != generation:
+            raise RuntimeError(
+                "stale CLIP activations: another encode_image/forward_patches call with batch size %d ran on this tower between this "
+                "forward (generation %d) and its backward (workspace now holds generation %d).  The tower keeps ONE set of saved "
+                "activations per batch size; differentiate each embedding batch before embedding the next one of the same size "
+                "(sample.py:199-214 does exactly that)." % (n, generation, ws["generation"]))
         g2, D, T, E = self.grid ** 2, self.width, self.tokens, self.output_dim
         M = n * T
-        ws = self._ws[n]
         P, C = _lib.ptr, _lib.call
         demb = demb.contiguous().float()
         C("cg_vit_proj_bwd", P(demb), P(self.proj), n, D, E, P(ws["dy"]))
@@ -230,12 +245,13 @@ class _EncodeImageFn(torch.autograd.Function):
         _lib.call("cg_patchify_fwd", _lib.ptr(img), n, cs, tower.patch, tower.kpad, int(normalize), _lib.ptr(patches))
         emb = tower.forward_patches(patches)
         ctx.tower, ctx.normalize, ctx.shape, ctx.dtype = tower, normalize, image.shape, image.dtype
+        ctx.generation = tower._generation
         return emb
 
     @staticmethod
     def backward(ctx, demb):
         tower = ctx.tower
-        dpatch = tower.backward_patches(demb)
+        dpatch = tower.backward_patches(demb, generation=ctx.generation)
         n, _, cs, _ = ctx.shape
         dimg = torch.empty(ctx.shape, device=demb.device, dtype=torch.float32)
         _lib.call("cg_patchify_bwd", _lib.ptr(dpatch), 1, n, cs, tower.patch, tower.kpad, int(ctx.normalize), _lib.ptr(dimg))
@@ -285,20 +301,42 @@ class CLIPModelB200:
         return self
 
 
-def load_clip_models(model_names, device=None):
-    """models.py:74-84.  Weights: ``$CLIPGUIDE_B200_WEIGHTS/<name with / -> _>.pt`` (OpenAI key naming) when present,
-    else seeded random init (there is no network on the benchmark boxes)."""
+def load_clip_models(model_names, device=None, allow_random_init=False):
+    """models.py:74-84.  Weights: ``$CLIPGUIDE_B200_WEIGHTS/<name with / -> _>.pt``, a state dict in OpenAI's key naming
+    (``visual.conv1.weight`` ...; what ``clip.load(name).state_dict()`` holds).  A missing directory or file is an ERROR --
+    guidance with random weights is meaningless -- unless the caller opts in with ``allow_random_init=True`` (benchmarks and
+    tests: there is no network on the benchmark boxes, and throughput does not depend on the weight values)."""
     device = device or "cuda"
     wdir = os.environ.get("CLIPGUIDE_B200_WEIGHTS")
     models = {}
     for i, name in enumerate(model_names):
+        if name not in CLIP_CONFIGS:
+            raise ValueError("unsupported CLIP model %r: this path implements the ViT towers %s" % (name, sorted(CLIP_CONFIGS)))
         sd = None
-        if wdir:
-            path = os.path.join(wdir, name.replace("/", "_") + ".pt")
-            if os.path.exists(path):
-                sd = torch.load(path, map_location="cpu")
+        path = os.path.join(wdir, name.replace("/", "_") + ".pt") if wdir else None
+        if path and os.path.exists(path):
+            sd = torch.load(path, map_location="cpu")
+            missing = [k for k in random_clip_state_dict_keys(name) if k not in sd]
+            if missing:
+                raise KeyError("%s lacks %d visual-tower keys (first: %s): expected OpenAI CLIP naming" % (path, len(missing), missing[0]))
+        elif not allow_random_init:
+            raise FileNotFoundError(
+                "no weights for %r: set CLIPGUIDE_B200_WEIGHTS to a directory holding %s.pt (OpenAI CLIP state dict), or pass "
+                "allow_random_init=True for benchmarking with seeded random weights" % (name, name.replace("/", "_")))
         models[name] = CLIPModelB200(name, sd, device, seed=1 + i)
     return models
+
+
+def random_clip_state_dict_keys(name):
+    """The ``visual.*`` keys the tower reads from a state dict."""
+    _, _, _, layers, _, _ = CLIP_CONFIGS[name]
+    keys = ["visual.conv1.weight", "visual.class_embedding", "visual.positional_embedding", "visual.proj", "visual.ln_pre.weight",
+            "visual.ln_pre.bias", "visual.ln_post.weight", "visual.ln_post.bias"]
+    for i in range(layers):
+        p = "visual.transformer.resblocks.%d." % i
+        keys += [p + k for k in ("attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias", "mlp.c_fc.weight",
+                                 "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias", "ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias")]
+    return keys
 
 
 class LinearAestheticPredictor(nn.Module):

@@ -198,24 +198,25 @@ class GuidanceStep:
         p_mean_var = self.diffusion.p_mean_variance(self.model, x, ts, clip_denoised=False, model_kwargs={"y": y})
         return self._guidance_from_prediction(x, p_mean_var)
 
-    def ddim_step(self, x, i, eta=0.0, denoised_fn=None, clip_denoised=False, reuse_forward=True):
+    def ddim_step(self, x, i, eta=0.0, denoised_fn=None, clip_denoised=False, reuse_forward=True, noise=None):
         """One guided DDIM step (what the sampler generator does per iteration, sample.py:241-287).
 
         reuse_forward=True: the reference evaluates the UNet twice at the same (x, t) -- once
         without grad inside the sampler's p_mean_variance and once with grad inside cond_fn (sample.py:149-151).  Both
-        give the same numbers, so ONE grad-enabled forward serves both; results are identical to the two-forward path."""
+        give the same numbers, so ONE grad-enabled forward serves both; results are identical to the two-forward path.
+        ``noise`` replaces the sampler's ``randn_like`` draw (parity tests feed both sides the same tensor)."""
         self.current_timestep = i
         t = torch.full((x.shape[0],), i, device=x.device, dtype=torch.long)
         if not reuse_forward:
             return self.diffusion.ddim_sample(self.model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=self.cond_fn,
-                                              model_kwargs={}, eta=eta)
+                                              model_kwargs={}, eta=eta, noise=noise)
         with torch.enable_grad():
             xg = x.detach().requires_grad_()
             p_mean_var = self.diffusion.p_mean_variance(self.model, xg, t, clip_denoised=False, model_kwargs={"y": None})
             guidance = self._guidance_from_prediction(xg, p_mean_var)
         with torch.no_grad():
             out_orig = self.diffusion.finish_p_mean_variance(x, t, p_mean_var["pred_xstart"].detach(), clip_denoised, denoised_fn)
-        return self.diffusion.ddim_sample(self.model, x, t, cond_fn=lambda *_a, **_k: guidance, model_kwargs={}, eta=eta, out_orig=out_orig)
+        return self.diffusion.ddim_sample(self.model, x, t, cond_fn=lambda *_a, **_k: guidance, model_kwargs={}, eta=eta, out_orig=out_orig, noise=noise)
 
     def _guidance_from_prediction(self, x, p_mean_var):
         cfg = self.config

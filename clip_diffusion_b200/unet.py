@@ -308,6 +308,17 @@ class UNetModel(nn.Module):
                     if isinstance(mod, (nn.Conv1d, nn.Conv2d)):  # as guided-diffusion: convs only, Linear stays fp32
                         mod.half()
 
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        invalidate_weight_caches(self)  # cached fused biases / embedding projection were built from the old weights
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if "_emb_cat" in self.__dict__:
+            invalidate_weight_caches(self)
+        return out
+
     def _project_embeddings(self, emb):
         """All ResBlocks' `emb_layers` (SiLU -> Linear(emb_ch, 2C)) as ONE fp32 GEMV over the concatenated weights instead of 49 SiLU +
         49 GEMV launches of ~7 us each (the timestep embedding is the same for every block; weights are frozen, so the
@@ -343,6 +354,9 @@ class UNetModel(nn.Module):
             h = self.out_norm(h, silu=True, out_dtype=x.dtype)  # fp32 statistics and fp32 output from the fp16 trunk, one pass
         else:
             h = self.out_norm(h.type(x.dtype), silu=True)
+        if self._emb_cat is not None:
+            for blk in self._emb_cat[0]:
+                blk._scale_shift = None  # per-forward slices: a ResBlock called on its own must not reuse them
         return self.out_conv(h)
 
 
@@ -367,6 +381,60 @@ def create_unet(image_size=512, seed=2, device="cuda", use_fp16=True, config=Non
             if isinstance(mod, (GroupNorm32, Resample)):
                 mod.nhwc = True
     return model
+
+
+_GD_RENAMES = (  # ours -> crowsonkb/guided-diffusion (the module the reference builds at models.py:90-117)
+    (".in_norm.", ".in_layers.0."), (".in_conv.", ".in_layers.2."), (".emb.", ".emb_layers.1."), (".out_norm.", ".out_layers.0."),
+    (".out_conv.", ".out_layers.3."), (".skip.", ".skip_connection."), (".proj.", ".proj_out."),
+)
+
+
+def guided_diffusion_key(ours):
+    """Name of one of this UNet's parameters in a guided-diffusion ``UNetModel`` state dict (the checkpoint the reference loads
+    with ``model.load_state_dict(torch.load(...))``, models.py:118-124)."""
+    if ours.startswith("out_norm."):
+        return "out.0." + ours[len("out_norm."):]
+    if ours.startswith("out_conv."):
+        return "out.2." + ours[len("out_conv."):]
+    key = ours.replace(".layers.", ".")  # our _Seq wraps a ModuleList; guided-diffusion's TimestepEmbedSequential indexes directly
+    for a, b in _GD_RENAMES:
+        key = key.replace(a, b)
+    return key
+
+
+def invalidate_weight_caches(model):
+    """The fused NHWC path caches tensors derived from the (frozen) weights: the concatenated embedding projection of all
+    ResBlocks, each ResBlock's deferred biases and the per-forward scale-shift slices.  Call after changing weights in place;
+    ``load_state_dict`` / ``_apply`` (``.to``, ``.half``...) do it automatically."""
+    model._emb_cat = None
+    for mod in model.modules():
+        if isinstance(mod, ResBlock):
+            mod._fused_bias = None
+            mod._scale_shift = None
+
+
+def load_guided_diffusion_state_dict(model, state_dict, strict=True):
+    """Load a guided-diffusion checkpoint (512x512_diffusion_uncond_finetune_008100.pt and friends, models.py:118-124) into this
+    UNet: same tensors, renamed (``guided_diffusion_key``).  Conv1d qkv/proj weights keep their [out, in, 1] shape.  Raises on
+    missing / unexpected / mis-shaped entries when ``strict``."""
+    own = model.state_dict()
+    mapped, missing = {}, []
+    for ours, ref in own.items():
+        src = guided_diffusion_key(ours)
+        if src not in state_dict:
+            missing.append(src)
+            continue
+        t = state_dict[src]
+        if tuple(t.shape) != tuple(ref.shape):
+            raise ValueError("%s: checkpoint shape %s != model shape %s (%s)" % (src, tuple(t.shape), tuple(ref.shape), ours))
+        mapped[ours] = t
+    unexpected = sorted(set(state_dict) - {guided_diffusion_key(k) for k in own})
+    if strict and (missing or unexpected):
+        raise KeyError("guided-diffusion checkpoint does not match this UNet: %d missing (first %s), %d unexpected (first %s)"
+                       % (len(missing), missing[:1], len(unexpected), unexpected[:1]))
+    result = model.load_state_dict(mapped, strict=False)
+    invalidate_weight_caches(model)
+    return result
 
 
 def graph_unet(model, height, width=None, device="cuda"):

@@ -4,10 +4,6 @@ import torch
 
 from clip_diffusion_b200 import _lib
 
-# bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream:
-# entries are (flops, start_event, end_event).
-PROFILE = None
-
 
 def gemm_bf16_tn(a, b, epilogue, bias=None, out=None, aux=None, pos=None, g2=0, m=None):
     """acc[M,N] = a[M,K] @ b[N,K]^T with a fused epilogue (see CG_EPI_* in the header).  a, b: bf16 row-major
@@ -26,14 +22,8 @@ def gemm_bf16_tn(a, b, epilogue, bias=None, out=None, aux=None, pos=None, g2=0, 
         out = torch.empty(M, N, device=a.device, dtype=dt)
     if epilogue == _lib.EPI_BIAS_QGELU_BF16 and aux is None:
         aux = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
-    if PROFILE is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
     _lib.call(
         "cg_gemm_bf16_tn", _lib.ptr(a), _lib.ptr(b), M, N, K, a.stride(0), b.stride(0), epilogue, _lib.ptr(bias), _lib.ptr(out),
         _lib.ptr(aux), out.stride(0), _lib.ptr(pos), g2,
     )
-    if PROFILE is not None:
-        ev1.record()
-        PROFILE.append((2.0 * M * N * K, ev0, ev1))
     return (out, aux) if epilogue == _lib.EPI_BIAS_QGELU_BF16 else out

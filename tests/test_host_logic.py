@@ -197,3 +197,64 @@ def test_ms_ssim_restatement_properties():
     assert 0.0 < loss.item() < 1.0 and torch.isfinite(gr).all() and gr.abs().max().item() > 0
     with pytest.raises(ValueError):
         ms_ssim(x[..., :100, :100], y[..., :100, :100])
+
+
+def test_guided_diffusion_checkpoint_key_mapping_covers_the_whole_unet():
+    """the reference loads a guided-diffusion checkpoint with model.load_state_dict (models.py:118-124); the key
+    mapping must cover every parameter of this UNet, follow guided-diffusion's naming and round-trip the tensors."""
+    from clip_diffusion_b200.unet import create_unet, guided_diffusion_key, load_guided_diffusion_state_dict
+
+    m = create_unet(64, seed=2, device="cpu", use_fp16=False)
+    own = m.state_dict()
+    gd = {guided_diffusion_key(k): torch.randn(v.shape, generator=torch.Generator().manual_seed(i)) for i, (k, v) in enumerate(own.items())}
+    assert len(gd) == len(own), "two parameters map to the same guided-diffusion key"
+    # guided-diffusion naming landmarks (SURVEY.md App. A.3)
+    for key in ("time_embed.0.weight", "time_embed.2.bias", "input_blocks.0.0.weight", "input_blocks.1.0.in_layers.0.weight",
+                "input_blocks.1.0.in_layers.2.weight", "input_blocks.1.0.emb_layers.1.weight", "input_blocks.1.0.out_layers.0.bias",
+                "input_blocks.1.0.out_layers.3.weight", "middle_block.1.norm.weight", "middle_block.1.qkv.weight", "middle_block.1.proj_out.weight",
+                "middle_block.0.in_layers.2.bias", "out.0.weight", "out.2.weight"):
+        assert key in gd, key
+    assert any(k.endswith("skip_connection.weight") for k in gd)
+    assert not any(".layers." in k or ".in_norm." in k or ".emb." in k for k in gd)
+    load_guided_diffusion_state_dict(m, gd)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, gd[guided_diffusion_key(k)]), k
+    bad = dict(gd)
+    bad.pop("out.2.weight")
+    with pytest.raises(KeyError):
+        load_guided_diffusion_state_dict(m, bad)
+    bad = dict(gd)
+    bad["out.2.weight"] = torch.zeros(1)
+    with pytest.raises(ValueError):
+        load_guided_diffusion_state_dict(m, bad)
+
+
+def test_unet_weight_caches_are_invalidated_by_load_state_dict():
+    from clip_diffusion_b200.unet import ResBlock, create_unet
+
+    m = create_unet(32, seed=2, device="cpu", use_fp16=False)
+    m._emb_cat = ("stale",)
+    blocks = [b for b in m.modules() if isinstance(b, ResBlock)]
+    blocks[0]._fused_bias = ("stale",)
+    m.load_state_dict(m.state_dict())
+    assert m._emb_cat is None and blocks[0]._fused_bias is None
+    m._emb_cat = ("stale",)
+    m.float()
+    assert m._emb_cat is None
+
+
+def test_missing_clip_weights_are_an_error_unless_random_init_is_requested(tmp_path, monkeypatch):
+    from clip_diffusion_b200 import models
+
+    monkeypatch.delenv("CLIPGUIDE_B200_WEIGHTS", raising=False)
+    with pytest.raises(FileNotFoundError):
+        models.load_clip_models(["ViT-B/32"], "cpu")
+    monkeypatch.setenv("CLIPGUIDE_B200_WEIGHTS", str(tmp_path))
+    with pytest.raises(FileNotFoundError):
+        models.load_clip_models(["ViT-B/32"], "cpu")
+    torch.save({"visual.conv1.weight": torch.zeros(1)}, str(tmp_path / "ViT-B_32.pt"))
+    with pytest.raises(KeyError):
+        models.load_clip_models(["ViT-B/32"], "cpu")
+    with pytest.raises(ValueError):
+        models.load_clip_models(["RN101"], "cpu", allow_random_init=True)
+    assert set(models.random_clip_state_dict_keys("ViT-B/32")) == set(models.random_clip_state_dict("ViT-B/32"))

@@ -98,7 +98,9 @@ def _tower_pair(name, n):
     return mine, ref, img
 
 
-@pytest.mark.parametrize("name,n", [("test-tiny/32", 4), ("test-small/16", 3), ("test-k/14", 5), ("ViT-B/32", 2)])
+# the real towers at full size (random init): these are the shapes bench.py runs (c2 = ViT-B/16, target = ViT-L/14, c5 = ViT-L/14@336px)
+@pytest.mark.parametrize("name,n", [("test-tiny/32", 4), ("test-small/16", 3), ("test-k/14", 5), ("ViT-B/32", 2), ("ViT-B/16", 4), ("ViT-L/14", 2),
+                                    ("ViT-L/14@336px", 1)])
 def test_tower_embedding_and_input_gradient(name, n):
     from clip_diffusion_b200.utils.functional import embed_image
     from oracle.cutouts import clip_normalize
@@ -175,3 +177,25 @@ print("WORST", worst)
     res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CG_ATTN_TC="1"), capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "WORST" in res.stdout
+
+
+def test_stale_workspace_backward_raises_instead_of_wrong_gradients():
+    """the saved activations live in ONE workspace per (tower, batch size).  Two same-size forwards followed by the
+    backward of the first must raise (generation id), never silently differentiate against the second forward's activations."""
+    from clip_diffusion_b200.utils.functional import embed_image
+
+    mine, _, img = _tower_pair("test-tiny/32", 3)
+    a = img.cuda().requires_grad_()
+    b = (1 - img).cuda().requires_grad_()
+    ea = embed_image(mine, a)
+    eb = embed_image(mine, b)  # same batch size: overwrites the saved activations of `ea`
+    (gb,) = torch.autograd.grad(eb.sum(), b)  # latest forward: fine
+    assert torch.isfinite(gb).all()
+    with pytest.raises(RuntimeError, match="stale CLIP activations"):
+        torch.autograd.grad(ea.sum(), a)
+    # sequential use (sample.py:199-214: differentiate each batch before embedding the next) keeps working
+    ea = embed_image(mine, a)
+    (ga,) = torch.autograd.grad(ea.sum(), a)
+    eb = embed_image(mine, b)
+    (gb2,) = torch.autograd.grad(eb.sum(), b)
+    assert torch.equal(gb, gb2) and torch.isfinite(ga).all()
