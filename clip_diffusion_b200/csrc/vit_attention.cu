@@ -424,12 +424,14 @@ static int pick_warps(int T) {
   return best;
 }
 
-int cg_attention_fwd_tc(const void* qkv, int Nimg, int T, int heads, void* ctx, float* lse, cudaStream_t s);  // vit_attention_tc.cu
+// vit_attention_tc.cu: tcgen05/TMEM kernels for T <= 272; return 1 when they do not apply
+int cg_attention_fwd_tc(const void* qkv, int Nimg, int T, int heads, void* ctx, float* lse, cudaStream_t s);
+int cg_attention_bwd_tc(const void* qkv, const void* dctx, const float* lse, const float* delta, int Nimg, int T, int heads, void* dqkv, cudaStream_t s);
 
 extern "C" int cg_attention_fwd(const void* qkv, int Nimg, int T, int heads, void* ctx, float* lse, void* stream) {
   CG_REQUIRE(qkv && ctx && lse && Nimg > 0 && T > 0 && heads > 0, "cg_attention_fwd: bad arguments");
   {
-    // tcgen05/TMEM path for T <= 272 (all 224-pixel towers); returns 1 when it does not apply (T too long or CG_ATTN_TC=0)
+    // tcgen05/TMEM path for T <= 272 (all 224-pixel towers, the default); returns 1 when it does not apply (T too long or CG_ATTN_TC=0)
     const int rc_tc = cg_attention_fwd_tc(qkv, Nimg, T, heads, ctx, lse, cg_stream(stream));
     if (rc_tc != 1) return rc_tc;
   }
@@ -456,6 +458,10 @@ extern "C" int cg_attention_bwd(const void* qkv, const void* ctx, const void* dc
   attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(ctx), reinterpret_cast<const __nv_bfloat16*>(dctx), T, heads,
                                                                rows, delta_ws);
   CG_LAUNCH_CHECK();
+  {
+    const int rc_tc = cg_attention_bwd_tc(qkv, dctx, lse, delta_ws, Nimg, T, heads, dqkv, s);
+    if (rc_tc != 1) return rc_tc;
+  }
   const int W = pick_warps(T);
   const size_t smem_q = (size_t)(2 * Tp) * 128 + (size_t)W * 4096;
   int rc = set_smem(attn_bwd_dq_kernel, smem_q);

@@ -45,8 +45,10 @@ def test_layernorm_fwd_bwd(M, D, stride):
         assert (dx[:, D:] == 3.0).all()
 
 
-@pytest.mark.parametrize("n,T,heads", [(3, 50, 2), (2, 197, 12), (1, 257, 16), (1, 577, 4), (5, 5, 2), (2, 64, 3), (2, 65, 1)])
+@pytest.mark.parametrize("n,T,heads", [(3, 50, 2), (2, 197, 12), (1, 257, 16), (1, 577, 4), (5, 5, 2), (2, 64, 3), (2, 65, 1), (1, 128, 2), (1, 129, 2),
+                                       (2, 256, 2), (1, 272, 1), (3, 257, 4), (1, 16, 1), (2, 192, 2), (2, 193, 1)])
 def test_attention_fwd_bwd(n, T, heads):
+    """Default path: tcgen05/TMEM kernels (vit_attention_tc.cu) for T <= 272, mma.sync kernels beyond (T = 577)."""
     _lib = _lib_ops()
     D = heads * 64
     g = torch.Generator().manual_seed(T + heads)
@@ -142,9 +144,9 @@ def test_patchify_roundtrip():
     assert (back - img).abs().max().item() < 4e-3  # bf16 rounding of values in [0,1]
 
 
-def test_tcgen05_attention_forward_in_subprocess():
-    """The experimental tcgen05/TMEM attention forward (CG_ATTN_TC=1; S and O accumulators in TMEM, P staged as the smem A
-    operand, V as an MN-major B operand) against torch on the same bf16 inputs."""
+def test_mma_sync_attention_fallback_in_subprocess():
+    """CG_ATTN_TC=0 selects the legacy mma.sync kernels (vit_attention.cu; the default only beyond T = 272): kept parity-green
+    for A/B measurements against the tcgen05 path."""
     import os
     import subprocess
     import sys
@@ -155,26 +157,33 @@ sys.path.insert(0, %r)
 from clip_diffusion_b200 import _lib
 P = _lib.ptr
 worst = 0.0
-for (n, T, heads) in [(3, 50, 2), (2, 197, 12), (2, 257, 16), (5, 5, 2), (2, 64, 3), (2, 65, 1), (1, 128, 2), (1, 129, 2), (1, 272, 1)]:
+for (n, T, heads) in [(3, 50, 2), (2, 197, 12), (2, 257, 16), (5, 5, 2), (2, 65, 1)]:
     D = heads * 64
     g = torch.Generator().manual_seed(T + heads)
     qkv = (torch.randn(n * T, 3 * D, generator=g) * 0.8).bfloat16()
-    q, k, v = [t.float().view(n, T, heads, 64).transpose(1, 2) for t in qkv.split(D, dim=1)]
+    dctx = (torch.randn(n * T, D, generator=g) * 0.5).bfloat16()
+    q, k, v = [t.float().view(n, T, heads, 64).transpose(1, 2).requires_grad_() for t in qkv.split(D, dim=1)]
     s = (q @ k.transpose(-1, -2)) * 0.125
     ref = torch.softmax(s, -1) @ v
-    lse_ref = torch.logsumexp(s, -1)
-    qc = qkv.cuda()
+    do = dctx.float().view(n, T, heads, 64).transpose(1, 2)
+    grads = torch.autograd.grad((ref * do).sum(), (q, k, v))
+    qc, dc = qkv.cuda(), dctx.cuda()
     ctx = torch.full((n * T, D), float("nan"), device="cuda", dtype=torch.bfloat16)
     lse = torch.full((n, heads, T), float("nan"), device="cuda")
     _lib.call("cg_attention_fwd", P(qc), n, T, heads, P(ctx), P(lse))
     out = ctx.float().cpu().view(n, T, heads, 64).transpose(1, 2)
-    e1 = ((out - ref).abs().max() / ref.abs().max().clamp_min(1)).item()
-    e2 = (lse.cpu() - lse_ref).abs().max().item()
-    assert e1 < 2e-2 and e2 < 3e-3, (n, T, heads, e1, e2)
-    worst = max(worst, e1)
+    e1 = ((out - ref.detach()).abs().max() / ref.abs().max().clamp_min(1)).item()
+    assert e1 < 2e-2, (n, T, heads, e1)
+    dqkv = torch.full((n * T, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    delta = torch.empty(n, heads, T, device="cuda")
+    _lib.call("cg_attention_bwd", P(qc), P(ctx), P(dc), P(lse), n, T, heads, P(dqkv), P(delta))
+    for a, b in zip([t.float().cpu().view(n, T, heads, 64).transpose(1, 2) for t in dqkv.split(D, dim=1)], grads):
+        rel = ((a - b).norm() / b.norm()).item()
+        assert rel < 2e-2, (n, T, heads, rel)
+        worst = max(worst, rel)
 print("WORST", worst)
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CG_ATTN_TC="1"), capture_output=True, text=True, timeout=240)
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CG_ATTN_TC="0"), capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "WORST" in res.stdout
 
