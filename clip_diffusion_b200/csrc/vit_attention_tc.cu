@@ -6,27 +6,37 @@
 // One CTA per (image, head); everything the head needs is loaded ONCE by TMA into 128B-swizzled shared memory
 // (forward: Q, K, V; backward: Q, K, V, dO; <= 272 x 64 bf16 each), one mbarrier per 64-row block so the first MMAs
 // start while the rest is still in flight.  The work is cut into BLOCKS of 128 rows x 64 columns of the score matrix
-// and streamed through a pipeline with double-buffered TMEM and staging buffers:
+// and streamed through a pipeline with multi-buffered TMEM (S / dP blocks) and shared-memory staging buffers:
 //
-//   warp 1 (one thread)   tcgen05.mma   S_blk = A_tile B_blk^T (and dP_blk in the backward) into TMEM buffer b = g & 1,
-//                                       then, when the block's staged operand is ready, the accumulator MMA
-//                                       (O += P V | dQ += dS K | dV += P^T dO, dK += dS^T Q) with the B operand in MN-major form
-//   warps 4-7 / 8-11      softmax       two warpgroups, block g goes to warpgroup g & 1; a thread owns one row
-//                                       (= one TMEM lane): tcgen05.ld, exp2 / dS arithmetic in registers, bf16 result
-//                                       written to the staging buffer in the K-major 128B-swizzled operand layout
-//   warps 12-15           epilogue      tcgen05.ld of the finished accumulator tile (double buffered) -> bf16 -> HBM
-//   warp 0                TMA producer, warp 2 TMEM allocation
+//   warps 0-3             tcgen05.mma   FOUR issuer warps (warp-converged loops, elect.sync lane).  With head_dim 64 the MMAs are
+//                                       small (128 x 64 x 16 = 32 tensor-pipe cycles) and a single issuing thread was the bottleneck
+//                                       (measured ~1000 cycles per block).  forward: warps 0 / 1 = S of the even / odd blocks, warp 2 =
+//                                       O += P V; backward: warp 0 = S (S^T), warp 1 = dP (dP^T), warp 2 = dQ | dV, warp 3 = dK.
+//                                       Accumulator MMAs take the staged operand as K-major A and V / K / dO / Q as MN-major B.
+//   warps 4-7 / 8-11      softmax       two warpgroups, block g goes to warpgroup g & 1; a thread owns one row (= one TMEM lane):
+//                                       tcgen05.ld, exp2 / dS arithmetic in registers, bf16 result written to the staging buffer in the
+//                                       K-major 128B-swizzled operand layout.  A tile with ONE real row (T = 128 k + 1: the ViT-L/14
+//                                       sequence 257) is spread over the lanes of its warp through shared memory instead.
+//   warps 12-15           epilogue      tcgen05.ld of the finished accumulators -> bf16 -> HBM
+//   warp 0 lane 0         TMA producer (before the CTA-wide sync), warp 2 TMEM allocation
 //
-// so the tensor pipe computes block g+1 (and the accumulator MMA of block g-1) while a warpgroup is busy with the
-// MUFU-bound exponentials of block g.  All smem / TMEM operand forms are the ones vit_gemm.cu and the round-1 forward
-// validated: K-major SW128 A and B, MN-major SW128 B with N = 64.
+// All smem / TMEM operand forms are the ones vit_gemm.cu and the round-1 forward validated: K-major SW128 A and B, MN-major SW128 B
+// with N = 64.  Every mbarrier waiter sees every phase of its barrier (a parity wait is only sound then): warps without real rows
+// still arrive in step, and no consumer ever skips a use of a shared buffer.
 //
-//   forward   per 128-query tile: pass 0 streams S blocks for the row maximum, pass 1 recomputes them (the tensor pipe is
-//             idle otherwise), P = exp2((s - m) c) and O accumulates in TMEM with no rescaling; epilogue O / l, lse.
+//   forward   ONE pass, online softmax without a row-maximum pre-pass: each warpgroup keeps its own reference maximum and row sum
+//             and accumulates ITS blocks into ITS OWN O accumulator; the reference only moves when a block exceeds it by 2^8 (then
+//             the accumulator is rescaled in TMEM: tcgen05.ld / tcgen05.st); the epilogue merges the two partial results.
 //   backward  phase A (lane = query):  S = Q K^T, dP = dO V^T, dS = P (dP - delta) scale, dQ += dS K
 //             phase B (lane = key):    S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
 //             P is recomputed from the saved log-sum-exp; two orientations instead of a transposed smem operand, no atomics,
 //             deterministic.  Rows / columns beyond T are masked (tail block only) or never stored.
+//
+// Measured on B200 (profiles/r02_attention_*.txt), T = 257 x 64 images x 16 heads: forward 108 us, backward 232 us per layer (round 1
+// mma.sync kernels: 104 / 349).  A softmax warp spends ~2900 cycles per 64-column block of which the MUFU-bound share is 1024 (two warps
+// per SM sub-partition, 8 cycles per MUFU.EX2 warp instruction, measured with tools/probes/mufu_probe.cu): the tcgen05.ld latency, the
+// serial max chain, the proxy fence and the barrier round trips of the two warps of a sub-partition run in lock step and leave the MUFU
+// idle.  More softmax warps per sub-partition (register budget: 512 threads x 128) is the next step.
 #include <stdlib.h>
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -49,6 +59,28 @@ __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void st_shared_b16(uint32_t a, float v) {
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(*reinterpret_cast<const unsigned short*>(&b)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
 }
 // instruction descriptor, kind::f16: D fp32 (bit 4), A/B bf16 (bits 7, 10), b_major (bit 16: MN-major B), N>>3 at 17, M>>4 at 24
 __device__ __forceinline__ uint32_t idesc_bf16(int n, bool b_mn_major) {
@@ -83,36 +115,46 @@ __device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const uint3
   for (int j = 0; j < 4; ++j) st256g(dst + 16 * j, w + 8 * j);
 }
 
+// Pipeline depths.  S (and dP) blocks: 4 x 64 TMEM columns in the forward, 3 x 128 in the backward (the accumulators need the
+// rest of the 512 columns); staging buffers: 4 x 16 KB in the forward, 2 x 32 KB (P^T and dS^T) in the backward.
+template <bool FWD> struct Depth { static constexpr int NSB = FWD ? 4 : 3, NPB = FWD ? 4 : 2; };
+
 // barrier block (8 bytes each)
 struct Bars {
   uint32_t base;
-  __device__ __forceinline__ uint32_t sfull(int b) const { return base + 8u * b; }          // S (dP) block b is in TMEM           (tcgen05.commit)
-  __device__ __forceinline__ uint32_t sfree(int b) const { return base + 16u + 8u * b; }    // warpgroup b has read it             (4 warps)
-  __device__ __forceinline__ uint32_t pready(int b) const { return base + 32u + 8u * b; }   // staging buffer b is written          (4 warps)
-  __device__ __forceinline__ uint32_t pfree(int b) const { return base + 48u + 8u * b; }    // accumulator MMAs have consumed it    (tcgen05.commit)
-  __device__ __forceinline__ uint32_t accfull(int a) const { return base + 64u + 8u * a; }  // accumulator tile a is complete       (tcgen05.commit)
-  __device__ __forceinline__ uint32_t accfree(int a) const { return base + 80u + 8u * a; }  // epilogue has read it                 (4 warps)
-  __device__ __forceinline__ uint32_t lready(int a) const { return base + 96u + 8u * a; }   // forward: row sums / maxima in smem   (8 warps)
-  __device__ __forceinline__ uint32_t op(int o, int blk) const { return base + 112u + 8u * (o * MAX_BLK + blk); }  // operand o, 64-row block
-  __device__ __forceinline__ uint32_t tmem_slot() const { return base + 112u + 8u * (4 * MAX_BLK); }
+  __device__ __forceinline__ uint32_t sfull(int b) const { return base + 8u * b; }            // S (dP) block in TMEM buffer b          (tcgen05.commit)
+  __device__ __forceinline__ uint32_t sfree(int b) const { return base + 32u + 8u * b; }      // the owning warpgroup has read it        (4 warps)
+  __device__ __forceinline__ uint32_t pready(int b) const { return base + 64u + 8u * b; }     // staging buffer b is written             (4 warps)
+  __device__ __forceinline__ uint32_t pfree(int b) const { return base + 96u + 8u * b; }      // accumulator MMAs have consumed it       (tcgen05.commit)
+  __device__ __forceinline__ uint32_t accfull(int a) const { return base + 128u + 8u * a; }   // accumulator a is complete               (tcgen05.commit)
+  __device__ __forceinline__ uint32_t accfree(int a) const { return base + 152u + 8u * a; }   // epilogue has read it                    (4 warps)
+  __device__ __forceinline__ uint32_t lready(int t) const { return base + 176u + 8u * t; }    // forward: row sums of tile t are in smem (8 warps)
+  __device__ __forceinline__ uint32_t op(int o, int blk) const { return base + 200u + 8u * (o * MAX_BLK + blk); }  // operand o, 64-row block
+  __device__ __forceinline__ uint32_t tmem_slot() const { return base + 200u + 8u * (4 * MAX_BLK); }
 };
-constexpr uint32_t BARS_BYTES = 112 + 8 * 4 * MAX_BLK + 16;
+constexpr uint32_t BARS_BYTES = 200 + 8 * 4 * MAX_BLK + 16;
 
-// The block stream.  Every role (MMA issuer, the two softmax warpgroups, the epilogue warps) walks the SAME enumeration, so
-// buffer indices and mbarrier parities are derived identically everywhere.
+// The block stream.  Every role (the two MMA issuers, the two softmax warpgroups, the epilogue warps) walks the SAME enumeration,
+// so buffer indices and mbarrier parities are derived identically everywhere.
 //   backward: phase-major  (phase 0 = dQ with lane = query, phase 1 = dK/dV with lane = key) -> tile -> 64-wide block
 //   forward:  tile-major   tile -> pass (0 = row maximum, 1 = exponentials + O) -> block
 template <bool FWD>
 struct BlkIt {
   int phase = 0, tile = 0, blk = 0;
-  int g = 0;       // running block index: TMEM buffer = g & 1, use = g >> 1
-  int tcount = 0;  // running accumulator-tile index: accumulator buffer = tcount & 1, use = tcount >> 1
-  int su0 = 0, su1 = 0;  // staging-buffer use counters (forward: pass-0 blocks do not stage anything)
+  int g = 0;       // running block index: warpgroup = g & 1, TMEM buffer = g % NSB
+  int s = 0;       // running index of the blocks that stage an operand (forward: pass-1 blocks only): staging buffer = s % NPB
+  int tcount = 0;  // running accumulator-tile index
   __device__ __forceinline__ bool valid(int ntiles) const { return FWD ? tile < ntiles : phase < 2; }
   __device__ __forceinline__ bool stages() const { return !FWD || phase == 1; }
-  __device__ __forceinline__ int su() const { return (g & 1) ? su1 : su0; }
+  __device__ __forceinline__ int sbuf() const { return g % Depth<FWD>::NSB; }
+  __device__ __forceinline__ uint32_t suse() const { return (uint32_t)(g / Depth<FWD>::NSB); }
+  __device__ __forceinline__ int pbuf() const { return s % Depth<FWD>::NPB; }
+  __device__ __forceinline__ uint32_t puse() const { return (uint32_t)(s / Depth<FWD>::NPB); }
+  // accumulator slot and its use count: forward / backward phase A alternate two slots; phase B (dV + dK = 128 columns) has one
+  __device__ __forceinline__ int acc() const { return (!FWD && phase == 1) ? 2 : (tcount & 1); }
+  __device__ __forceinline__ uint32_t ause() const { return (uint32_t)((!FWD && phase == 1) ? tile : (tcount >> 1)); }
   __device__ __forceinline__ void next(int ntiles, int nblk) {
-    if (stages()) { if (g & 1) ++su1; else ++su0; }
+    if (stages()) ++s;
     ++g;
     if (++blk < nblk) return;
     blk = 0;
@@ -132,10 +174,25 @@ struct AttnParams {
   float* lse;                // [Nimg, heads, T]  (forward out, backward in)
   const float* delta;        // backward in [Nimg, heads, T]
   __nv_bfloat16* dqkv;       // backward out [Nimg*T, 3D]
+  long long* trace;          // debug: clock64() time line of CTA (0,0) (tools/trace_attn.py); nullptr in production
 };
+// time-line probe (compiled in with -DCG_ATTN_TRACE only): slot = role, idx = block, ev = event
+#ifdef CG_ATTN_TRACE
+#define TR(slot, idx, ev)                                                                                   \
+  do {                                                                                                      \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0)                \
+      p.trace[(((slot) * 64 + (idx)) << 3) + (ev)] = clock64();                                             \
+  } while (0)
+#else
+#define TR(slot, idx, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ int blk_cols(const AttnParams& p, int blk) { return blk == p.nblk - 1 ? p.T - blk * 64 : 64; }
 __device__ __forceinline__ int blk_cols16(const AttnParams& p, int blk) { return blk == p.nblk - 1 ? p.tail_rows : 64; }
+
+// TMEM columns
+template <bool FWD> __device__ __forceinline__ uint32_t s_col(int sbuf) { return (uint32_t)(FWD ? sbuf * 64 : sbuf * 128); }
+template <bool FWD> __device__ __forceinline__ uint32_t acc_col(int a) { return FWD ? 256u + 64u * a : (a == 2 ? 384u : 384u + 64u * a); }
 
 // operands in shared memory: 0 = Q, 1 = K, 2 = V, 3 = dO
 template <bool FWD>
@@ -144,6 +201,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
                    const __grid_constant__ CUtensorMap tmDOtail, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int NOPS = FWD ? 3 : 4;
+  constexpr int NSB = Depth<FWD>::NSB, NPB = Depth<FWD>::NPB;
   constexpr uint32_t STAGE_BYTES = FWD ? TILE_BYTES : 2 * TILE_BYTES;  // backward phase B stages P^T and dS^T
   const int T = p.T, D = p.heads * 64;
   const int h = blockIdx.x, n = blockIdx.y;
@@ -152,14 +210,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sOp0 = base;
   const uint32_t sStage = base + NOPS * opb;                    // 1024-aligned; also absorbs the A-operand over-read of the last tile
-  const uint32_t sF = sStage + 2 * STAGE_BYTES;                 // float scratch
+  const uint32_t sF = sStage + NPB * STAGE_BYTES;               // float scratch
   float* fscr = reinterpret_cast<float*>(smem_raw + (sF - smem_u32(smem_raw)));
   // forward: smax[2][128] (per warpgroup partial row maxima), sl[3][2][128] (tile, warpgroup: partial row sums), smf[3][128] (final row
   // maxima per tile; T <= 272 -> <= 3 tiles, so nothing is ever overwritten while the epilogue may still read it)
   // backward: nlse[320], delta[320]
-  constexpr uint32_t FSCR_FLOATS = FWD ? (256 + 768 + 384) : 640;
+  constexpr uint32_t FSCR_FLOATS = FWD ? (256 + 768 + 384) : (640 + 256);  // backward: + [2][128] scratch of the 1-row tiles
   Bars bars{sF + FSCR_FLOATS * 4};
   const int row0 = n * T;  // first row of this image in the packed [Nimg*T, 3D] qkv matrix
+  const int ntiles = p.ntiles, nblk = p.nblk;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
@@ -168,13 +227,37 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDOtail) : "memory");
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bars.sfull(b), 1); mbar_init(bars.sfree(b), 4); mbar_init(bars.pready(b), 4); mbar_init(bars.pfree(b), 1);
-      mbar_init(bars.accfull(b), 1); mbar_init(bars.accfree(b), 4); mbar_init(bars.lready(b), 8);
-    }
+    // backward: two issuer warps feed every block (S and dP) and two drain every staging buffer (dQ | dV and dK): their barriers count 2
+    constexpr uint32_t NISS = FWD ? 1 : 2;
+    for (int b = 0; b < 4; ++b) { mbar_init(bars.sfull(b), NISS); mbar_init(bars.sfree(b), 4); mbar_init(bars.pready(b), 4); mbar_init(bars.pfree(b), NISS); }
+    for (int a = 0; a < 3; ++a) { mbar_init(bars.accfull(a), NISS); mbar_init(bars.accfree(a), 4); mbar_init(bars.lready(a), 8); }
     for (int o = 0; o < 4; ++o)
       for (int k = 0; k < MAX_BLK; ++k) mbar_init(bars.op(o, k), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // ================= TMA producer: every operand block once, in the order the MMA issuers need them; issued before the CTA-wide
+    // sync below (only this thread has touched the barriers so far) so the loads overlap the TMEM allocation
+    auto load = [&](int o, int blk) {
+      const bool tail = blk == nblk - 1;
+      const uint32_t bytes = (uint32_t)(tail ? p.tail_rows : 64) * 128u;
+      const uint32_t dst = sOp0 + o * opb + blk * BLK_BYTES;
+      const uint32_t bar = bars.op(o, blk);
+      mbar_arrive_expect_tx(bar, bytes);
+      if (o < 3) tma_load_2d(dst, tail ? &tmQKVtail : &tmQKV, bar, o * D + h * 64, row0 + blk * 64);
+      else tma_load_2d(dst, tail ? &tmDOtail : &tmDO, bar, h * 64, row0 + blk * 64);
+    };
+    const int first = nblk < 2 ? nblk : 2;
+    load(1, 0);
+    for (int k = 0; k < first; ++k) load(0, k);
+    if (FWD) {
+      for (int k = 1; k < nblk; ++k) load(1, k);
+      for (int k = 0; k < nblk; ++k) load(2, k);
+      for (int k = first; k < nblk; ++k) load(0, k);
+    } else {
+      load(2, 0);
+      for (int k = 0; k < first; ++k) load(3, k);
+      for (int k = 1; k < nblk; ++k) { load(1, k); load(2, k); }
+      for (int k = first; k < nblk; ++k) { load(0, k); load(3, k); }
+    }
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512) : "memory");
@@ -194,222 +277,378 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars.tmem_slot()) : "memory");
-  // TMEM columns: S (dP) buffers b at b*128 (+64); accumulators from column 256: forward O[a] at 256 + 64a; backward phase A dQ[a] at
-  // 256 + 128a, phase B dV[a] at 256 + 128a and dK[a] at 256 + 128a + 64
-  const int ntiles = p.ntiles, nblk = p.nblk;
+  TR(warp, 63, 2);
 
-  if (warp == 0) {
-    // ================= TMA producer: every operand block once, in the order the MMA issuer needs them
-    if (lane == 0) {
-      auto load = [&](int o, int blk) {
-        const bool tail = blk == nblk - 1;
-        const uint32_t bytes = (uint32_t)(tail ? p.tail_rows : 64) * 128u;
-        const uint32_t dst = sOp0 + o * opb + blk * BLK_BYTES;
-        const uint32_t bar = bars.op(o, blk);
-        mbar_arrive_expect_tx(bar, bytes);
-        if (o < 3) tma_load_2d(dst, tail ? &tmQKVtail : &tmQKV, bar, o * D + h * 64, row0 + blk * 64);
-        else tma_load_2d(dst, tail ? &tmDOtail : &tmDO, bar, h * 64, row0 + blk * 64);
-      };
-      const int first = nblk < 2 ? nblk : 2;
-      load(1, 0);
-      for (int k = 0; k < first; ++k) load(0, k);
-      if (FWD) {
-        for (int k = 1; k < nblk; ++k) load(1, k);
-        for (int k = 0; k < nblk; ++k) load(2, k);
-        for (int k = first; k < nblk; ++k) load(0, k);
-      } else {
-        load(2, 0);
-        for (int k = 0; k < first; ++k) load(3, k);
-        for (int k = 1; k < nblk; ++k) { load(1, k); load(2, k); }
-        for (int k = first; k < nblk; ++k) { load(0, k); load(3, k); }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer
-    if (lane == 0) {
-      uint32_t loaded = 0;  // operand blocks already seen complete (bit o*MAX_BLK + blk)
-      auto need = [&](int o, int blk) {
-        const uint32_t bit = 1u << (o * MAX_BLK + blk);
-        if (!(loaded & bit)) { mbar_wait(bars.op(o, blk), 0); loaded |= bit; }
-      };
-      auto need_tile = [&](int o, int tile) { need(o, 2 * tile); if (2 * tile + 1 < nblk) need(o, 2 * tile + 1); };
-      const uint32_t id_acc = idesc_bf16(64, true);
-      // S (and dP) of one block into TMEM buffer b
-      auto issue_s = [&](const BlkIt<FWD>& it) {
-        const int b = it.g & 1;
-        mbar_wait(bars.sfree(b), (uint32_t)(((it.g >> 1) & 1) ^ 1));
-        const bool transposed = !FWD && it.phase == 1;
-        const int oa = transposed ? 1 : 0, ob = transposed ? 0 : 1;  // S: A rows (tile) x B rows (block)
-        need_tile(oa, it.tile); need(ob, it.blk);
-        if (!FWD) { need_tile(transposed ? 2 : 3, it.tile); need(transposed ? 3 : 2, it.blk); }
-        tcgen05_fence_after();
-        const uint32_t idesc = idesc_bf16(blk_cols16(p, it.blk), false);
-        const uint32_t d_s = tmem_base + (uint32_t)(b * 128);
-        const uint64_t ad = make_smem_desc(sOp0 + oa * opb + it.tile * TILE_BYTES), bd = make_smem_desc(sOp0 + ob * opb + it.blk * BLK_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(d_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
-        if (!FWD) {
-          const int oa2 = transposed ? 2 : 3, ob2 = transposed ? 3 : 2;  // dP = dO V^T | dP^T = V dO^T
-          const uint64_t ad2 = make_smem_desc(sOp0 + oa2 * opb + it.tile * TILE_BYTES), bd2 = make_smem_desc(sOp0 + ob2 * opb + it.blk * BLK_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d_s + 64u, ad2 + (uint64_t)(2 * k), bd2 + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
-        }
-        umma_commit(bars.sfull(b));
-      };
-      // accumulator MMAs of one block from staging buffer b
-      auto issue_acc = [&](const BlkIt<FWD>& it) {
-        if (!it.stages()) return;
-        const int b = it.g & 1, a = it.tcount & 1;
-        mbar_wait(bars.pready(b), (uint32_t)(it.su() & 1));
-        if (it.blk == 0) mbar_wait(bars.accfree(a), (uint32_t)(((it.tcount >> 1) & 1) ^ 1));
-        tcgen05_fence_after();
-        const int ksteps = blk_cols16(p, it.blk) >> 4;
-        const uint32_t stage = sStage + b * STAGE_BYTES;
+  if (warp < 4) {
+    // ================= four MMA issuer warps.  tcgen05.mma is issued by ONE thread, and with head_dim 64 the instructions are small
+    // (128 x 64 x 16: 32 tensor-pipe cycles), so a single issuing thread is the bottleneck (measured: ~1000 cycles per block).  The
+    // issue work is therefore spread over four warps, each running a lean, warp-converged loop with an elected lane:
+    //   forward   warp 0: S of the even blocks (warpgroup 0)   warp 1: S of the odd blocks      warp 2: O += P V               warp 3: idle
+    //   backward  warp 0: S (S^T) of every block               warp 1: dP (dP^T) of every block  warp 2: dQ | dV      warp 3: (-) | dK
+    // Different issuers never touch the same accumulator; everything else is ordered through the mbarriers.
+    const uint32_t elected = elect_one();
+    uint32_t loaded = 0;  // operand blocks already seen complete (bit o*MAX_BLK + blk)
+    auto need = [&](int o, int blk) {
+      const uint32_t bit = 1u << (o * MAX_BLK + blk);
+      if (!(loaded & bit)) { mbar_wait(bars.op(o, blk), 0); loaded |= bit; }
+    };
+    auto need_tile = [&](int o, int tile) { need(o, 2 * tile); if (2 * tile + 1 < nblk) need(o, 2 * tile + 1); };
+    const int per_tile = FWD ? 2 * nblk : nblk, per_phase = ntiles * nblk;
+    const int G = FWD ? ntiles * per_tile : 2 * per_phase;
+    const uint32_t id_full = idesc_bf16(64, false), id_tail = idesc_bf16(p.tail_rows, false), id_acc = idesc_bf16(64, true);
+    if (warp < 2) {
+      // ---- S-type MMAs: D[128 x ncols] = A_tile[128 x 64] . B_blk[ncols x 64]^T, 4 k-steps of 16
+      const int g0 = FWD ? warp : 0, gstep = FWD ? 2 : 1;
+      for (int g = g0; g < G; g += gstep) {
+        int phase, tile, blk;
         if (FWD) {
-          const uint32_t d_o = tmem_base + 256u + (uint32_t)(a * 64);
-          for (int s = 0; s < ksteps; ++s)
-            umma_bf16(d_o, make_smem_desc(stage) + (uint64_t)(2 * s), make_smem_desc(sOp0 + 2 * opb + it.blk * BLK_BYTES + s * 2048), id_acc,
-                      (it.blk | s) != 0 ? 1u : 0u);
-        } else if (it.phase == 0) {
-          const uint32_t d_q = tmem_base + 256u + (uint32_t)(a * 128);
-          for (int s = 0; s < ksteps; ++s)  // dQ += dS K
-            umma_bf16(d_q, make_smem_desc(stage) + (uint64_t)(2 * s), make_smem_desc(sOp0 + 1 * opb + it.blk * BLK_BYTES + s * 2048), id_acc,
-                      (it.blk | s) != 0 ? 1u : 0u);
+          tile = g / per_tile;
+          const int r = g - tile * per_tile;
+          phase = r >= nblk ? 1 : 0;
+          blk = r - phase * nblk;
         } else {
-          const uint32_t d_v = tmem_base + 256u + (uint32_t)(a * 128), d_k = d_v + 64u;
-          for (int s = 0; s < ksteps; ++s) {  // dV += P^T dO ; dK += dS^T Q
-            umma_bf16(d_v, make_smem_desc(stage) + (uint64_t)(2 * s), make_smem_desc(sOp0 + 3 * opb + it.blk * BLK_BYTES + s * 2048), id_acc,
-                      (it.blk | s) != 0 ? 1u : 0u);
-            umma_bf16(d_k, make_smem_desc(stage + TILE_BYTES) + (uint64_t)(2 * s), make_smem_desc(sOp0 + 0 * opb + it.blk * BLK_BYTES + s * 2048), id_acc,
-                      (it.blk | s) != 0 ? 1u : 0u);
+          phase = g >= per_phase ? 1 : 0;
+          const int r = g - phase * per_phase;
+          tile = r / nblk;
+          blk = r - tile * nblk;
+        }
+        const int b = g % NSB;
+        const bool transposed = !FWD && phase == 1;
+        // forward / backward warp 0: S = Q K^T (S^T = K Q^T);  backward warp 1: dP = dO V^T (dP^T = V dO^T)
+        const int oa = (FWD || warp == 0) ? (transposed ? 1 : 0) : (transposed ? 2 : 3);
+        const int ob = (FWD || warp == 0) ? (transposed ? 0 : 1) : (transposed ? 3 : 2);
+        need_tile(oa, tile);
+        need(ob, blk);
+        mbar_wait(bars.sfree(b), ((uint32_t)(g / NSB) & 1u) ^ 1u);
+        TR(warp, g, 0);
+        tcgen05_fence_after();
+        const uint32_t d_s = tmem_base + s_col<FWD>(b) + ((!FWD && warp == 1) ? 64u : 0u);
+        const uint64_t ad = make_smem_desc(sOp0 + oa * opb + tile * TILE_BYTES), bd = make_smem_desc(sOp0 + ob * opb + blk * BLK_BYTES);
+        const uint32_t idesc = blk == nblk - 1 ? id_tail : id_full;
+        if (elected) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+          umma_commit(bars.sfull(b));
+        }
+        __syncwarp();
+        TR(warp, g, 1);
+      }
+    } else {
+      // ---- accumulator MMAs of the staged blocks: D[128 x 64] += A_stage[128 x ncols] . B_blk[ncols x 64] (B in MN-major form)
+      // (forward: ONE accumulator issuer.  Splitting the tiles over two issuers would make each of them skip uses of the shared staging
+      // buffers, and an mbarrier parity wait is only sound for a waiter that sees every phase.)
+      const int w = warp - 2;
+      for (int g = (FWD && w != 0) ? G : 0; g < G; ++g) {
+        int phase, tile, blk, sidx, a;
+        uint32_t ause;
+        if (FWD) {
+          tile = g / per_tile;
+          const int r = g - tile * per_tile;
+          phase = r >= nblk ? 1 : 0;
+          if (phase == 0) { g += nblk - 1; continue; }  // pass 0 stages nothing: skip to the tile's pass-1 blocks
+          blk = r - nblk;
+          sidx = tile * nblk + blk;
+          a = tile & 1;
+          ause = (uint32_t)(tile >> 1);
+        } else {
+          phase = g >= per_phase ? 1 : 0;
+          const int r = g - phase * per_phase;
+          tile = r / nblk;
+          blk = r - tile * nblk;
+          sidx = g;
+          a = phase == 1 ? 2 : (tile & 1);
+          ause = (uint32_t)(phase == 1 ? tile : (tile >> 1));
+        }
+        const int pb = sidx % NPB;
+        const bool does_mma = FWD || phase == 1 || w == 0;
+        // B operand: forward V; backward phase A K, phase B dO (warp 2: dV) / Q (warp 3: dK)
+        const int ob = FWD ? 2 : (phase == 0 ? 1 : (w == 0 ? 3 : 0));
+        if (does_mma) need(ob, blk);
+        mbar_wait(bars.pready(pb), (uint32_t)(sidx / NPB) & 1u);
+        TR(warp, g, 0);
+        if (blk == 0) {
+          mbar_wait(bars.accfree(a), (ause & 1u) ^ 1u);
+          if (!FWD && phase == 1 && tile == 0) {
+            // slot 2 (dV | dK) overlays the two dQ slots of phase A: every phase-A tile must have left TMEM first
+            const int u0 = (ntiles + 1) / 2, u1 = ntiles / 2;
+            mbar_wait(bars.accfree(0), (uint32_t)((u0 - 1) & 1));
+            if (u1 > 0) mbar_wait(bars.accfree(1), (uint32_t)((u1 - 1) & 1));
           }
         }
-        umma_commit(bars.pfree(b));
-        if (it.blk == nblk - 1) umma_commit(bars.accfull(a));
-      };
-      BlkIt<FWD> is, ia;
-      for (int k = 0; k < 2 && is.valid(ntiles); ++k) { issue_s(is); is.next(ntiles, nblk); }
-      while (ia.valid(ntiles)) {
-        if (is.valid(ntiles)) { issue_s(is); is.next(ntiles, nblk); }
-        issue_acc(ia);
-        ia.next(ntiles, nblk);
+        tcgen05_fence_after();
+        const int ksteps = (blk == nblk - 1 ? p.tail_rows : 64) >> 4;
+        const uint32_t stage = sStage + pb * STAGE_BYTES + ((!FWD && w == 1) ? TILE_BYTES : 0u);  // warp 3: dS^T (second staged tile)
+        const uint32_t d_acc = tmem_base + acc_col<FWD>(a) + ((!FWD && w == 1) ? 64u : 0u);
+        const uint64_t ad = make_smem_desc(stage), bd = make_smem_desc(sOp0 + ob * opb + blk * BLK_BYTES);
+        const bool last = blk == nblk - 1;
+        if (elected) {
+          if (does_mma) {
+            for (int k = 0; k < ksteps; ++k) umma_bf16(d_acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(128 * k), id_acc, (blk | k) != 0 ? 1u : 0u);
+            umma_commit(bars.pfree(pb));
+            if (last) umma_commit(bars.accfull(a));
+          } else {  // backward phase A, warp 3: nothing to multiply, keep the two-arrival barriers in step
+            mbar_arrive(bars.pfree(pb));
+            if (last) mbar_arrive(bars.accfull(a));
+          }
+        }
+        __syncwarp();
+        TR(warp, g, 1);
       }
     }
   } else if (warp >= 4 && warp < 12) {
-    // ================= softmax warpgroups: block g belongs to warpgroup g & 1; thread = one row (TMEM lane) of the tile
+    // ================= softmax warpgroups: block g belongs to warpgroup g & 1; thread = one row (TMEM lane) of the tile.
+    // Each warpgroup enumerates ITS blocks directly (g = wg, wg + 2, ...) and decodes (phase, tile, blk) with a few integer ops.
     const int wg = (warp - 4) >> 2;
     const int q = warp & 3;
     const int rl = q * 32 + lane;  // row inside the 128-row tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float sl2 = p.scale * LOG2E_F;
+    const float scale = p.scale, sl2 = p.scale * LOG2E_F;
+    const int tail_cols = T - (nblk - 1) * 64, tail_cols16 = p.tail_rows;
     float rc0 = 0.f, rc1 = 0.f;     // backward phase A: -lse*log2e and delta of this row; forward: m*c and the running sum
-    float mx = -INFINITY;            // forward pass 0: running maximum of this warpgroup's blocks
+    float mx = -INFINITY;            // forward pass 0: running maximum of this warpgroup's blocks of the current tile
     float* smax = fscr;              // [2][128]
     float* sl = fscr + 256;          // [3][2][128]
     float* smf = fscr + 1024;        // [3][128]
-    int cur_tile = -1, cur_phase = -1;
-    for (BlkIt<FWD> it; it.valid(ntiles); it.next(ntiles, nblk)) {
-      const int row = it.tile * 128 + rl;
-      const bool wvalid = it.tile * 128 + q * 32 < T;  // warp-uniform: this warp has at least one real row
+    // staging-tile addressing: row rl, 16-byte chunk (4h + j) ^ (rl & 7) = (4h ^ (x & 4)) | (j ^ (x & 3))
+    const uint32_t srow = (uint32_t)rl * 128u, sx = (uint32_t)(rl & 7);
+    const uint32_t shalf0 = srow + (((0u ^ (sx & 4u))) << 4), shalf1 = srow + (((4u ^ (sx & 4u))) << 4);
+    const uint32_t so0 = ((0u ^ (sx & 3u)) << 4), so1 = ((1u ^ (sx & 3u)) << 4), so2 = ((2u ^ (sx & 3u)) << 4), so3 = ((3u ^ (sx & 3u)) << 4);
+    auto stage32 = [&](uint32_t tile_base, int c0, const uint32_t* w) {
+      const uint32_t hb = tile_base + (c0 ? shalf1 : shalf0);
+      st_shared_v4(hb + so0, w[0], w[1], w[2], w[3]);
+      st_shared_v4(hb + so1, w[4], w[5], w[6], w[7]);
+      st_shared_v4(hb + so2, w[8], w[9], w[10], w[11]);
+      st_shared_v4(hb + so3, w[12], w[13], w[14], w[15]);
+    };
+    const int per_tile = FWD ? 2 * nblk : nblk, per_phase = ntiles * nblk;
+    const int G = FWD ? ntiles * per_tile : 2 * per_phase;
+    int synced = 0, finished = 0;  // forward: tiles whose pass-0 maxima have been combined / whose row sums have been published
+    // forward, once per tile and warpgroup (whether or not it owns blocks of that pass): combine the pass-0 maxima of both warpgroups ...
+    auto sync_tile = [&](int t) {
+      smax[wg * 128 + rl] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float m = fmaxf(smax[rl], smax[128 + rl]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // smax may be overwritten by the next tile only after everybody has read it
+      rc0 = m * sl2;
+      rc1 = 0.f;
+      mx = -INFINITY;
+      if (wg == 0) smf[t * 128 + rl] = m;
+    };
+    // ... and publish this warpgroup's partial row sums of the tile to the epilogue warps
+    auto finish_tile = [&](int t) {
+      sl[(t * 2 + wg) * 128 + rl] = rc1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars.lready(t));
+    };
+    int cur_tile = -1;
+    for (int g = wg; g < G; g += 2) {
+      int phase, tile, blk, sidx;
       if (FWD) {
-        if (it.blk == 0 && it.phase == 0) { mx = -INFINITY; }
-        if (it.blk == 0 && it.phase == 1) {
-          // both warpgroups have finished pass 0 of this tile: combine the partial maxima
-          smax[wg * 128 + rl] = mx;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const float m = fmaxf(smax[rl], smax[128 + rl]);
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // smax may be overwritten by the next tile only after everybody has read it
-          rc0 = m * sl2;
-          rc1 = 0.f;
-          if (wg == 0) smf[it.tile * 128 + rl] = m;
+        tile = g / per_tile;
+        const int r = g - tile * per_tile;
+        phase = r >= nblk ? 1 : 0;
+        blk = r - phase * nblk;
+        sidx = tile * nblk + blk;
+        while (finished < tile) {
+          if (synced <= finished) { sync_tile(finished); ++synced; }
+          finish_tile(finished);
+          ++finished;
         }
-      } else if (it.phase == 0 && (it.tile != cur_tile || it.phase != cur_phase)) {
-        const bool ok = row < T;
-        rc0 = ok ? -p.lse[((long long)n * p.heads + h) * T + row] * LOG2E_F : 0.f;
-        rc1 = ok ? p.delta[((long long)n * p.heads + h) * T + row] : 0.f;
+        if (phase == 1 && synced <= tile) { sync_tile(tile); ++synced; }
+      } else {
+        phase = g >= per_phase ? 1 : 0;
+        const int r = g - phase * per_phase;
+        tile = r / nblk;
+        blk = r - tile * nblk;
+        sidx = g;
+        if (phase == 0 && tile != cur_tile) {
+          const int row = tile * 128 + rl;
+          const bool ok = row < T;
+          rc0 = ok ? -p.lse[((long long)n * p.heads + h) * T + row] * LOG2E_F : 0.f;
+          rc1 = ok ? p.delta[((long long)n * p.heads + h) * T + row] : 0.f;
+          cur_tile = tile;
+        }
       }
-      cur_tile = it.tile; cur_phase = it.phase;
-      const bool last_of_tile_pass = it.blk == nblk - 1;
-      if ((it.g & 1) == wg) {
-        const int b = wg;
-        const int ncols = blk_cols(p, it.blk), ncols16 = blk_cols16(p, it.blk);
-        const bool tail = it.blk == nblk - 1;
-        mbar_wait(bars.sfull(b), (uint32_t)((it.g >> 1) & 1));
-        tcgen05_fence_after();
-        const uint32_t t_s = t_lane + (uint32_t)(b * 128);
-        if (FWD && it.phase == 0) {
-          if (wvalid) {
-            for (int c0 = 0; c0 < ncols16; c0 += 32) {
-              uint32_t sv[32];
-              tmem_ld32(t_s + (uint32_t)c0, sv);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (!tail || c0 + j < ncols) mx = fmaxf(mx, __uint_as_float(sv[j]));
-            }
-          }
+      const bool wvalid = tile * 128 + q * 32 < T;  // warp-uniform: this warp has at least one real row
+      const bool tail = blk == nblk - 1;
+      const int ncols = tail ? tail_cols : 64, ncols16 = tail ? tail_cols16 : 64;
+      const int b = g % NSB;
+      const uint32_t suse = (uint32_t)(g / NSB);
+      TR(warp, g, 0);
+      mbar_wait(bars.sfull(b), suse & 1u);
+      TR(warp, g, 1);
+      tcgen05_fence_after();
+      const uint32_t t_s = t_lane + s_col<FWD>(b);
+      if (FWD && phase == 0) {
+        if (wvalid) {
+          uint32_t sv[64];
+          tmem_ld32(t_s, sv);
+          if (ncols16 > 32) tmem_ld32(t_s + 32u, sv + 32);
+          tmem_ld_wait();
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bars.sfree(b));
-        } else {
-          const uint32_t stage = sStage + b * STAGE_BYTES;
-          bool waited = false;
-          if (wvalid) {
-            for (int c0 = 0; c0 < ncols16; c0 += 32) {
-              uint32_t sv[32], dv[32], w0[16], w1[16];
-              tmem_ld32(t_s + (uint32_t)c0, sv);
-              if (!FWD) tmem_ld32(t_s + 64u + (uint32_t)c0, dv);
-              tmem_ld_wait();
-              if (c0 + 32 >= ncols16) {  // last TMEM read of this block: release the buffer before the arithmetic
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars.sfree(b));
-              }
-              if (FWD) {
+          if (!tail) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  float p0 = ex2f(fmaf(__uint_as_float(sv[2 * j]), sl2, -rc0)), p1 = ex2f(fmaf(__uint_as_float(sv[2 * j + 1]), sl2, -rc0));
-                  if (tail) { if (c0 + 2 * j >= ncols) p0 = 0.f; if (c0 + 2 * j + 1 >= ncols) p1 = 0.f; }
-                  rc1 += p0 + p1;
-                  w0[j] = pack_bf2(p0, p1);
-                }
-              } else if (it.phase == 0) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  float p0 = ex2f(fmaf(__uint_as_float(sv[2 * j]), sl2, rc0)), p1 = ex2f(fmaf(__uint_as_float(sv[2 * j + 1]), sl2, rc0));
-                  if (tail) { if (c0 + 2 * j >= ncols) p0 = 0.f; if (c0 + 2 * j + 1 >= ncols) p1 = 0.f; }
-                  w0[j] = pack_bf2(p0 * p.scale * (__uint_as_float(dv[2 * j]) - rc1), p1 * p.scale * (__uint_as_float(dv[2 * j + 1]) - rc1));
-                }
-              } else {
-                const float* nl = fscr + it.blk * 64 + c0;  // per-query constants: broadcast reads
-                const float* dl = fscr + 320 + it.blk * 64 + c0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float2 l2 = *reinterpret_cast<const float2*>(nl + 2 * j), d2 = *reinterpret_cast<const float2*>(dl + 2 * j);
-                  const float p0 = ex2f(fmaf(__uint_as_float(sv[2 * j]), sl2, l2.x)), p1 = ex2f(fmaf(__uint_as_float(sv[2 * j + 1]), sl2, l2.y));
-                  w0[j] = pack_bf2(p0, p1);
-                  w1[j] = pack_bf2(p0 * p.scale * (__uint_as_float(dv[2 * j]) - d2.x), p1 * p.scale * (__uint_as_float(dv[2 * j + 1]) - d2.y));
-                }
-              }
-              if (!waited) { mbar_wait(bars.pfree(b), (uint32_t)((it.su() & 1) ^ 1)); waited = true; }  // staging buffer free again
-              stage_store32(stage, rl, c0, w0);
-              if (!FWD && it.phase == 1) stage_store32(stage + TILE_BYTES, rl, c0, w1);
-            }
+            for (int j = 0; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
           } else {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars.sfree(b));
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (j < ncols) mx = fmaxf(mx, __uint_as_float(sv[j]));
           }
-          fence_proxy_async_smem();  // generic-proxy writes of the staged operand -> visible to the tensor core (async proxy)
+        } else {
+          tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bars.pready(b));
+          if (lane == 0) mbar_arrive(bars.sfree(b));
+        }
+        TR(warp, g, 3);
+        continue;
+      }
+      const int pb = sidx % NPB;
+      const uint32_t puse = (uint32_t)(sidx / NPB);
+      const uint32_t stage = sStage + pb * STAGE_BYTES;
+      if (!wvalid) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.sfree(b));
+        // a warp without real rows stages nothing, but it must not run ahead of the barrier phases: its pready arrival for this use
+        // may only happen once the previous use of the staging buffer has been consumed (otherwise early arrivals of LATER blocks
+        // complete the current phase before the warp that does have rows has written its data)
+        mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u);
+      } else if (FWD) {
+        uint32_t sv[64], w[16];
+        tmem_ld32(t_s, sv);
+        if (ncols16 > 32) tmem_ld32(t_s + 32u, sv + 32);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.sfree(b));  // the S buffer is free for the block after next while the exponentials run
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          if (hlf * 32 < ncols16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float p0 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j]), sl2, -rc0)), p1 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j + 1]), sl2, -rc0));
+              if (tail) { if (hlf * 32 + 2 * j >= ncols) p0 = 0.f; if (hlf * 32 + 2 * j + 1 >= ncols) p1 = 0.f; }
+              rc1 += p0 + p1;
+              w[j] = pack_bf2(p0, p1);
+            }
+            if (hlf == 0) mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u);  // staging buffer free again
+            stage32(stage, hlf * 32, w);
+          }
+        }
+      } else if (!FWD && T - tile * 128 == 1) {
+        // ---- 1-row tile (T = 128 k + 1): lane 0 owns the only real row; it fetches S and dP from TMEM and hands them to the warp through
+        // shared memory, two columns per lane (a thread-per-row pass would cost the warp a full block of MUFU issue for one lane)
+        uint32_t sv[32], dv[32];
+        float* scr = fscr + 640 + wg * 128;
+        const int ncols = tail ? tail_cols : 64;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          tmem_ld32(t_s + (uint32_t)(32 * hlf), sv);
+          tmem_ld32(t_s + 64u + (uint32_t)(32 * hlf), dv);
+          tmem_ld_wait();
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              reinterpret_cast<uint4*>(scr + 32 * hlf)[j] = make_uint4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
+              reinterpret_cast<uint4*>(scr + 64 + 32 * hlf)[j] = make_uint4(dv[4 * j], dv[4 * j + 1], dv[4 * j + 2], dv[4 * j + 3]);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.sfree(b));
+        const bool va = lane < ncols, vb = lane + 32 < ncols;
+        const float s_a = scr[lane], s_b = scr[lane + 32], d_a = scr[64 + lane], d_b = scr[96 + lane];
+        __syncwarp();
+        float p_a, p_b, ds_a, ds_b;
+        if (phase == 0) {  // row = query 128 k: its lse / delta are in rc0 / rc1 of lane 0
+          const float c0 = __shfl_sync(0xffffffffu, rc0, 0), c1 = __shfl_sync(0xffffffffu, rc1, 0);
+          p_a = va ? ex2f(fmaf(s_a, sl2, c0)) : 0.f;
+          p_b = vb ? ex2f(fmaf(s_b, sl2, c0)) : 0.f;
+          ds_a = p_a * scale * (d_a - c1);
+          ds_b = p_b * scale * (d_b - c1);
+        } else {           // row = key 128 k, columns = queries of block blk (-inf in nlse masks the columns beyond T)
+          const float* nl = fscr + blk * 64;
+          p_a = ex2f(fmaf(s_a, sl2, nl[lane]));
+          p_b = ex2f(fmaf(s_b, sl2, nl[lane + 32]));
+          ds_a = p_a * scale * (d_a - nl[320 + lane]);
+          ds_b = p_b * scale * (d_b - nl[320 + lane + 32]);
+        }
+        mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u);  // staging buffer free again
+        // row 0 of the staged tile(s): no swizzle permutation.  Phase A stages dS; phase B stages P^T and dS^T.
+        st_shared_b16(stage + (uint32_t)lane * 2u, phase == 0 ? ds_a : p_a);
+        st_shared_b16(stage + 64u + (uint32_t)lane * 2u, phase == 0 ? ds_b : p_b);
+        if (phase == 1) {
+          st_shared_b16(stage + TILE_BYTES + (uint32_t)lane * 2u, ds_a);
+          st_shared_b16(stage + TILE_BYTES + 64u + (uint32_t)lane * 2u, ds_b);
+        }
+      } else {
+        // backward: S and dP in 16-column pieces, the loads of piece i+1 in flight while piece i is processed
+        uint32_t sv[2][16], dv[2][16], w0[8], w1[8];
+        const int npieces = ncols16 >> 4;
+        tmem_ld16(t_s, sv[0]);
+        tmem_ld16(t_s + 64u, dv[0]);
+        tmem_ld_wait();
+        bool waited = false;
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {
+          if (pc < npieces) {
+            const int cur = pc & 1;
+            if (pc + 1 < npieces) {
+              tmem_ld16(t_s + (uint32_t)(16 * (pc + 1)), sv[cur ^ 1]);
+              tmem_ld16(t_s + 64u + (uint32_t)(16 * (pc + 1)), dv[cur ^ 1]);
+            }
+            if (phase == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float p0 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j]), sl2, rc0)), p1 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j + 1]), sl2, rc0));
+                if (tail) { if (16 * pc + 2 * j >= ncols) p0 = 0.f; if (16 * pc + 2 * j + 1 >= ncols) p1 = 0.f; }
+                w0[j] = pack_bf2(p0 * scale * (__uint_as_float(dv[cur][2 * j]) - rc1), p1 * scale * (__uint_as_float(dv[cur][2 * j + 1]) - rc1));
+              }
+            } else {
+              const float* nl = fscr + blk * 64 + 16 * pc;  // per-query constants: broadcast reads
+              const float* dl = nl + 320;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 l2 = *reinterpret_cast<const float2*>(nl + 2 * j), d2 = *reinterpret_cast<const float2*>(dl + 2 * j);
+                const float p0 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j]), sl2, l2.x)), p1 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j + 1]), sl2, l2.y));
+                w0[j] = pack_bf2(p0, p1);
+                w1[j] = pack_bf2(p0 * scale * (__uint_as_float(dv[cur][2 * j]) - d2.x), p1 * scale * (__uint_as_float(dv[cur][2 * j + 1]) - d2.y));
+              }
+            }
+            if (!waited) { mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u); waited = true; }  // staging buffer free again
+            {
+              const uint32_t hb = stage + ((pc & 2) ? shalf1 : shalf0);
+              st_shared_v4(hb + ((pc & 1) ? so2 : so0), w0[0], w0[1], w0[2], w0[3]);
+              st_shared_v4(hb + ((pc & 1) ? so3 : so1), w0[4], w0[5], w0[6], w0[7]);
+              if (phase == 1) {
+                st_shared_v4(hb + TILE_BYTES + ((pc & 1) ? so2 : so0), w1[0], w1[1], w1[2], w1[3]);
+                st_shared_v4(hb + TILE_BYTES + ((pc & 1) ? so3 : so1), w1[4], w1[5], w1[6], w1[7]);
+              }
+            }
+            if (pc + 1 < npieces) {
+              tmem_ld_wait();
+            } else {  // every TMEM read of this block has completed (the wait of the previous piece covered this one's loads)
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bars.sfree(b));
+            }
+          }
         }
       }
-      if (FWD && it.phase == 1 && last_of_tile_pass) {
-        // this warpgroup is done with the tile (its last block of pass 1 is staged, or it had none): publish its partial row sums
-        sl[(it.tile * 2 + wg) * 128 + rl] = rc1;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars.lready(it.tcount & 1));
+      TR(warp, g, 2);
+      fence_proxy_async_smem();  // generic-proxy writes of the staged operand -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars.pready(pb));
+      TR(warp, g, 3);
+    }
+    if (FWD) {
+      while (finished < ntiles) {
+        if (synced <= finished) { sync_tile(finished); ++synced; }
+        finish_tile(finished);
+        ++finished;
       }
     }
   } else if (warp >= 12) {
@@ -421,16 +660,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     float* smf = fscr + 1024;
     const int total = FWD ? ntiles : 2 * ntiles;
     for (int tc = 0; tc < total; ++tc) {
-      const int a = tc & 1;
-      const uint32_t par = (uint32_t)((tc >> 1) & 1);
       const int phase = FWD ? 0 : tc / ntiles, tile = FWD ? tc : tc - phase * ntiles;
+      const int a = phase == 1 ? 2 : (tc & 1);
+      const uint32_t par = (uint32_t)((phase == 1 ? tile : (tc >> 1)) & 1);
       const int row = tile * 128 + rl;
       mbar_wait(bars.accfull(a), par);
-      if (FWD) mbar_wait(bars.lready(a), par);
+      if (FWD) mbar_wait(bars.lready(tile), 0);
+      TR(warp, tc, 0);
       tcgen05_fence_after();
       if (tile * 128 + q * 32 < T) {
         uint32_t v0[32], v1[32];
-        const uint32_t col = 256u + (uint32_t)(FWD ? a * 64 : a * 128);
+        const uint32_t col = acc_col<FWD>(a);
         tmem_ld32(t_lane + col, v0);
         tmem_ld32(t_lane + col + 32u, v1);
         tmem_ld_wait();
@@ -454,8 +694,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars.accfree(a));
+      TR(warp, tc, 1);
     }
   }
+  TR(warp, 63, 3);
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -463,6 +705,403 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
+
+// ------------------------------------------------------------------------------------------------ forward (online softmax)
+// One pass over the score blocks.  Block g = tile * nblk + blk goes to warpgroup g & 1; each warpgroup keeps ITS OWN running
+// reference maximum and row sum and accumulates its blocks into ITS OWN O accumulator in TMEM, so the two never wait for each
+// other; the epilogue merges the two partial results (flash-decoding style).  The reference maximum only moves when a block
+// exceeds it by more than 2^8 (P stays <= 256: exact in fp32 / bf16 range), in which case the warpgroup rescales its accumulator
+// in TMEM (tcgen05.ld / tcgen05.st) -- rare after the first block.
+//   TMEM: S buffers 4 x 64 columns [0, 256); O[wg][tile & 1] at 256 + (2 wg + (tile & 1)) * 64.
+struct FBars {
+  uint32_t base;
+  __device__ __forceinline__ uint32_t sfull(int b) const { return base + 8u * b; }
+  __device__ __forceinline__ uint32_t sfree(int b) const { return base + 32u + 8u * b; }
+  __device__ __forceinline__ uint32_t pready(int b) const { return base + 64u + 8u * b; }
+  __device__ __forceinline__ uint32_t pfree(int b) const { return base + 96u + 8u * b; }
+  __device__ __forceinline__ uint32_t accfull(int a) const { return base + 128u + 8u * a; }  // a = 2 wg + (tile & 1)
+  __device__ __forceinline__ uint32_t accfree(int a) const { return base + 160u + 8u * a; }
+  __device__ __forceinline__ uint32_t lready(int t) const { return base + 192u + 8u * t; }
+  __device__ __forceinline__ uint32_t op(int o, int blk) const { return base + 216u + 8u * (o * MAX_BLK + blk); }
+  __device__ __forceinline__ uint32_t tmem_slot() const { return base + 216u + 8u * (3 * MAX_BLK); }
+};
+constexpr uint32_t FBARS_BYTES = 216 + 8 * 3 * MAX_BLK + 16;
+constexpr float RESCALE_LOG2 = 8.f;
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+      "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+      "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+    attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKVtail, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int T = p.T, D = p.heads * 64;
+  const int h = blockIdx.x, n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = p.ntiles, nblk = p.nblk;
+  const uint32_t opb = (uint32_t)((nblk - 1) * 64 + p.tail_rows) * 128u;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sOp0 = base;                          // Q, K, V
+  const uint32_t sStage = base + 3 * opb;              // 4 x [128 x 64] bf16 P tiles
+  const uint32_t sF = sStage + 4 * TILE_BYTES;
+  float* fscr = reinterpret_cast<float*>(smem_raw + (sF - smem_u32(smem_raw)));
+  float* sm = fscr;         // [3][2][128] reference maxima (log2 units) per tile and warpgroup
+  float* sl = fscr + 768;   // [3][2][128] partial row sums
+  float* nscr = fscr + 1536;  // [2][64]: scores of a 1-row tile, spread over the lanes of the warp that owns the row
+  FBars bars{sF + (1536 + 128) * 4};
+  const int row0 = n * T;
+  const int G = ntiles * nblk;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKVtail) : "memory");
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(bars.sfull(b), 1); mbar_init(bars.sfree(b), 4); mbar_init(bars.pready(b), 4); mbar_init(bars.pfree(b), 1);
+      mbar_init(bars.accfull(b), 1); mbar_init(bars.accfree(b), 4);
+    }
+    for (int t = 0; t < 3; ++t) mbar_init(bars.lready(t), 8);
+    for (int o = 0; o < 3; ++o)
+      for (int k = 0; k < MAX_BLK; ++k) mbar_init(bars.op(o, k), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    auto load = [&](int o, int blk) {
+      const bool tail = blk == nblk - 1;
+      const uint32_t bar = bars.op(o, blk);
+      mbar_arrive_expect_tx(bar, (uint32_t)(tail ? p.tail_rows : 64) * 128u);
+      tma_load_2d(sOp0 + o * opb + blk * BLK_BYTES, tail ? &tmQKVtail : &tmQKV, bar, o * D + h * 64, row0 + blk * 64);
+    };
+    const int first = nblk < 2 ? nblk : 2;
+    load(1, 0);
+    for (int k = 0; k < first; ++k) load(0, k);
+    load(2, 0);
+    for (int k = 1; k < nblk; ++k) { load(1, k); load(2, k); }
+    for (int k = first; k < nblk; ++k) load(0, k);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars.tmem_slot()) : "memory");
+  TR(warp, 63, 2);
+
+  if (warp < 3) {
+    // ================= MMA issuers (warp-converged loops, elected lane): warp 0 / 1 = S of the even / odd blocks, warp 2 = O += P V
+    const uint32_t elected = elect_one();
+    uint32_t loaded = 0;
+    auto need = [&](int o, int blk) {
+      const uint32_t bit = 1u << (o * MAX_BLK + blk);
+      if (!(loaded & bit)) { mbar_wait(bars.op(o, blk), 0); loaded |= bit; }
+    };
+    const uint32_t id_full = idesc_bf16(64, false), id_tail = idesc_bf16(p.tail_rows, false), id_acc = idesc_bf16(64, true);
+    if (warp < 2) {
+      int tile = 0, blk = warp;  // block g = warp, warp + 2, ...
+      while (blk >= nblk) { blk -= nblk; ++tile; }
+      for (int g = warp; g < G; g += 2) {
+        const int b = g & 3;
+        need(0, 2 * tile);
+        if (2 * tile + 1 < nblk) need(0, 2 * tile + 1);
+        need(1, blk);
+        mbar_wait(bars.sfree(b), ((uint32_t)(g >> 2) & 1u) ^ 1u);
+        TR(warp, g, 0);
+        tcgen05_fence_after();
+        const uint32_t d_s = tmem_base + (uint32_t)(b * 64);
+        const uint64_t ad = make_smem_desc(sOp0 + tile * TILE_BYTES), bd = make_smem_desc(sOp0 + opb + blk * BLK_BYTES);
+        const uint32_t idesc = blk == nblk - 1 ? id_tail : id_full;
+        if (elected) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+          umma_commit(bars.sfull(b));
+        }
+        __syncwarp();
+        TR(warp, g, 1);
+        blk += 2;
+        while (blk >= nblk) { blk -= nblk; ++tile; }
+      }
+    } else {
+      int tile = 0, blk = 0;
+      for (int g = 0; g < G; ++g) {
+        const int pb = g & 3, wg = g & 1, a = 2 * wg + (tile & 1);
+        const bool first = blk < 2, last = blk + 2 >= nblk;  // first / last block of THIS warpgroup in the tile
+        need(2, blk);
+        mbar_wait(bars.pready(pb), (uint32_t)(g >> 2) & 1u);
+        TR(warp, g, 0);
+        if (first) mbar_wait(bars.accfree(a), ((uint32_t)(tile >> 1) & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_acc = tmem_base + 256u + (uint32_t)(a * 64);
+        const uint64_t ad = make_smem_desc(sStage + pb * TILE_BYTES), bd = make_smem_desc(sOp0 + 2 * opb + blk * BLK_BYTES);
+        if (elected) {
+          if (blk != nblk - 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(128 * k), id_acc, (!first || k != 0) ? 1u : 0u);
+          } else {
+            const int ksteps = p.tail_rows >> 4;
+            for (int k = 0; k < ksteps; ++k) umma_bf16(d_acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(128 * k), id_acc, (!first || k != 0) ? 1u : 0u);
+          }
+          umma_commit(bars.pfree(pb));
+          if (last) umma_commit(bars.accfull(a));
+        }
+        __syncwarp();
+        TR(warp, g, 1);
+        if (++blk == nblk) { blk = 0; ++tile; }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ================= softmax warpgroups
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int rl = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sl2 = p.scale * LOG2E_F;
+    const int tail_cols = T - (nblk - 1) * 64, tail_cols16 = p.tail_rows;
+    const uint32_t srow = (uint32_t)rl * 128u, sx = (uint32_t)(rl & 7);
+    const uint32_t shalf0 = srow + ((0u ^ (sx & 4u)) << 4), shalf1 = srow + ((4u ^ (sx & 4u)) << 4);
+    const uint32_t so0 = ((0u ^ (sx & 3u)) << 4), so1 = ((1u ^ (sx & 3u)) << 4), so2 = ((2u ^ (sx & 3u)) << 4), so3 = ((3u ^ (sx & 3u)) << 4);
+    float mref = -INFINITY, lsum = 0.f;  // running reference maximum (log2 units) and row sum of this warpgroup in the current tile
+    int cur_tile = -1, pub = 0;          // tile the state belongs to; tiles already published to the epilogue
+    auto publish_until = [&](int t_end) {
+      while (pub < t_end) {
+        const bool mine = pub == cur_tile;
+        sm[(pub * 2 + wg) * 128 + rl] = mine ? mref : -INFINITY;
+        sl[(pub * 2 + wg) * 128 + rl] = mine ? lsum : 0.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.lready(pub));
+        ++pub;
+      }
+    };
+    int tile = 0, blk = wg;
+    while (blk >= nblk) { blk -= nblk; ++tile; }
+    for (int g = wg; g < G; g += 2) {
+      const bool first = tile != cur_tile;
+      if (first) { publish_until(tile); cur_tile = tile; }
+      const bool wvalid = tile * 128 + q * 32 < T;
+      const bool rvalid = tile * 128 + rl < T;
+      const bool tail = blk == nblk - 1;
+      const int b = g & 3;                 // S buffer and staging buffer
+      const uint32_t use = (uint32_t)(g >> 2);
+      mbar_wait(bars.sfull(b), use & 1u);
+      TR(warp, g, 1);
+      tcgen05_fence_after();
+      if (!wvalid) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.sfree(b));
+        mbar_wait(bars.pfree(b), (use & 1u) ^ 1u);  // stay in step with the barrier phases (see the backward kernel)
+      } else if (T - tile * 128 == 1) {
+        // ---- 1-row tile (T = 128 k + 1: the ViT-L/14 sequence 257): a thread-per-row pass would cost the warp a full block of MUFU issue
+        // for a single lane.  Lane 0 fetches the row from TMEM and hands it to the warp through shared memory: two columns per lane.
+        uint32_t sv[64];
+        const uint32_t t_s = t_lane + (uint32_t)(b * 64);
+        const int ncols = tail ? tail_cols : 64;
+        tmem_ld32(t_s, sv);
+        tmem_ld32(t_s + 32u, sv + 32);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.sfree(b));
+        float* scr = nscr + wg * 64;
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) reinterpret_cast<uint4*>(scr)[j] = make_uint4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
+        }
+        __syncwarp();
+        const bool va = lane < ncols, vb = lane + 32 < ncols;
+        const float s_a = va ? scr[lane] * sl2 : -INFINITY, s_b = vb ? scr[lane + 32] * sl2 : -INFINITY;
+        __syncwarp();
+        const float bm = warp_max_f(fmaxf(s_a, s_b));
+        if (first) {
+          mref = bm;
+          lsum = 0.f;
+        } else if (bm > mref + RESCALE_LOG2) {  // warp-uniform
+          const int pbp = (g - 2) & 3;
+          mbar_wait(bars.pfree(pbp), (uint32_t)((g - 2) >> 2) & 1u);
+          tcgen05_fence_after();
+          const float f = ex2f(mref - bm);
+          const uint32_t t_o = t_lane + 256u + (uint32_t)((2 * wg + (tile & 1)) * 64);
+#pragma unroll
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(t_o + (uint32_t)c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+            tmem_st32(t_o + (uint32_t)c, o);
+          }
+          tmem_st_wait();
+          tcgen05_fence_before();
+          lsum *= f;
+          mref = bm;
+        }
+        const float p_a = ex2f(s_a - mref), p_b = ex2f(s_b - mref);  // ex2(-inf) = 0 for the masked columns
+        lsum += warp_sum(p_a + p_b);
+        mbar_wait(bars.pfree(b), (use & 1u) ^ 1u);  // staging buffer free again
+        const uint32_t srow0 = sStage + b * TILE_BYTES;  // row 0 of the tile: no swizzle permutation
+        st_shared_b16(srow0 + (uint32_t)lane * 2u, p_a);
+        st_shared_b16(srow0 + 64u + (uint32_t)lane * 2u, p_b);
+      } else {
+        uint32_t sv[64], w[16];
+        const uint32_t t_s = t_lane + (uint32_t)(b * 64);
+        const int ncols16 = tail ? tail_cols16 : 64;
+        tmem_ld32(t_s, sv);
+        if (ncols16 > 32) tmem_ld32(t_s + 32u, sv + 32);
+        tmem_ld_wait();
+        TR(warp, g, 0);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.sfree(b));
+        // block maximum over the valid columns
+        float bm = -INFINITY;
+        if (!tail) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) bm = fmaxf(bm, __uint_as_float(sv[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (j < tail_cols) bm = fmaxf(bm, __uint_as_float(sv[j]));
+        }
+        bm *= sl2;
+        TR(warp, g, 4);
+        if (first) {
+          mref = bm;
+          lsum = 0.f;
+        } else {
+          const bool grow = rvalid && bm > mref + RESCALE_LOG2;
+          if (__any_sync(0xffffffffu, grow)) {
+            // the reference moves: rescale this warpgroup's accumulator.  Its previous block (g - 2) must have left the tensor pipe.
+            const int pbp = (g - 2) & 3;
+            mbar_wait(bars.pfree(pbp), (uint32_t)((g - 2) >> 2) & 1u);
+            tcgen05_fence_after();
+            const float f = grow ? ex2f(mref - bm) : 1.f;
+            const uint32_t t_o = t_lane + 256u + (uint32_t)((2 * wg + (tile & 1)) * 64);
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+              uint32_t o[32];
+              tmem_ld32(t_o + (uint32_t)c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+              tmem_st32(t_o + (uint32_t)c, o);
+            }
+            tmem_st_wait();
+            tcgen05_fence_before();
+            lsum *= f;
+            if (grow) mref = bm;
+          }
+        }
+        bool waited = false;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          if (hlf * 32 < ncols16) {
+            float a0 = 0.f, a1 = 0.f;  // independent partial sums
+            if (!tail) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float p0 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j]), sl2, -mref)), p1 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j + 1]), sl2, -mref));
+                a0 += p0;
+                a1 += p1;
+                w[j] = pack_bf2(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float p0 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j]), sl2, -mref)), p1 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j + 1]), sl2, -mref));
+                if (hlf * 32 + 2 * j >= tail_cols) p0 = 0.f;
+                if (hlf * 32 + 2 * j + 1 >= tail_cols) p1 = 0.f;
+                a0 += p0;
+                a1 += p1;
+                w[j] = pack_bf2(p0, p1);
+              }
+            }
+            lsum += a0 + a1;
+            TR(warp, g, 5 + hlf);
+            if (!waited) { mbar_wait(bars.pfree(b), (use & 1u) ^ 1u); waited = true; }  // staging buffer free again
+            if (hlf == 0) TR(warp, g, 7);
+            const uint32_t hb = sStage + b * TILE_BYTES + (hlf ? shalf1 : shalf0);
+            st_shared_v4(hb + so0, w[0], w[1], w[2], w[3]);
+            st_shared_v4(hb + so1, w[4], w[5], w[6], w[7]);
+            st_shared_v4(hb + so2, w[8], w[9], w[10], w[11]);
+            st_shared_v4(hb + so3, w[12], w[13], w[14], w[15]);
+          }
+        }
+      }
+      TR(warp, g, 2);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars.pready(b));
+      TR(warp, g, 3);
+      blk += 2;
+      while (blk >= nblk) { blk -= nblk; ++tile; }
+    }
+    publish_until(ntiles);
+  } else if (warp >= 12) {
+    // ================= epilogue: merge the two warpgroups' partial results of a tile -> ctx (bf16), lse
+    const int q = warp & 3;
+    const int rl = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int tp = tile & 1;
+      const uint32_t par = (uint32_t)((tile >> 1) & 1);
+      // with a single block per tile only warpgroup (tile * nblk) & 1 takes part
+      const bool has0 = nblk > 1 || ((tile * nblk) & 1) == 0, has1 = nblk > 1 || ((tile * nblk) & 1) == 1;
+      mbar_wait(bars.lready(tile), 0);
+      if (has0) mbar_wait(bars.accfull(0 + tp), par);
+      if (has1) mbar_wait(bars.accfull(2 + tp), par);
+      TR(warp, tile, 0);
+      tcgen05_fence_after();
+      const int row = tile * 128 + rl;
+      if (tile * 128 + q * 32 < T) {
+        const float m0 = sm[(tile * 2 + 0) * 128 + rl], m1 = sm[(tile * 2 + 1) * 128 + rl];
+        const float l0 = sl[(tile * 2 + 0) * 128 + rl], l1 = sl[(tile * 2 + 1) * 128 + rl];
+        const float M = fmaxf(m0, m1);
+        const float f0 = has0 ? ex2f(m0 - M) : 0.f, f1 = has1 ? ex2f(m1 - M) : 0.f;
+        const float L = l0 * f0 + l1 * f1;
+        const float g0 = f0 / L, g1 = f1 / L;
+        __nv_bfloat16* dst = p.ctx + ((long long)(row0 + row)) * D + h * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t v0[32], v1[32], w[16];
+          if (has0) tmem_ld32(t_lane + 256u + (uint32_t)((0 + tp) * 64 + c), v0);
+          if (has1) tmem_ld32(t_lane + 256u + (uint32_t)((2 + tp) * 64 + c), v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a0 = (has0 ? __uint_as_float(v0[2 * j]) * g0 : 0.f) + (has1 ? __uint_as_float(v1[2 * j]) * g1 : 0.f);
+            const float a1 = (has0 ? __uint_as_float(v0[2 * j + 1]) * g0 : 0.f) + (has1 ? __uint_as_float(v1[2 * j + 1]) * g1 : 0.f);
+            w[j] = pack_bf2(a0, a1);
+          }
+          if (row < T) { st256g(dst + c, w); st256g(dst + c + 16, w + 8); }
+        }
+        if (row < T) p.lse[((long long)n * p.heads + h) * T + row] = M * (1.f / LOG2E_F) + logf(L);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (has0) mbar_arrive(bars.accfree(0 + tp));
+        if (has1) mbar_arrive(bars.accfree(2 + tp));
+      }
+      TR(warp, tile, 1);
+    }
+  }
+  TR(warp, 63, 3);
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+long long* g_trace = nullptr;
 
 int tc_enabled() {
   static int enabled = -1;
@@ -477,6 +1116,7 @@ template <bool FWD>
 int launch_attn_tc(const void* qkv, const void* dctx, int Nimg, int T, int heads, const AttnParams& p0, cudaStream_t s) {
   AttnParams p = p0;
   p.T = T; p.heads = heads; p.scale = 0.125f;
+  p.trace = g_trace;
   p.ntiles = (T + 127) / 128;
   p.nblk = (T + 63) / 64;
   p.tail_rows = ((T - (p.nblk - 1) * 64) + 15) & ~15;
@@ -494,7 +1134,7 @@ int launch_attn_tc(const void* qkv, const void* dctx, int Nimg, int T, int heads
     if (rc) return rc;
   }
   const size_t opb = (size_t)((p.nblk - 1) * 64 + p.tail_rows) * 128;
-  const size_t smem = 1024 + (FWD ? 3 : 4) * opb + 2 * (FWD ? TILE_BYTES : 2 * TILE_BYTES) + (FWD ? 1408 : 640) * 4 + BARS_BYTES;
+  const size_t smem = 1024 + (FWD ? 3 : 4) * opb + (size_t)Depth<FWD>::NPB * (FWD ? TILE_BYTES : 2 * TILE_BYTES) + (FWD ? 1408 : 640 + 256) * 4 + BARS_BYTES;
   static size_t configured = 0;
   if (smem > configured) {
     CG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -513,7 +1153,27 @@ int cg_attention_fwd_tc(const void* qkv, int Nimg, int T, int heads, void* ctx, 
   AttnParams p = {};
   p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
   p.lse = lse;
-  return launch_attn_tc<true>(qkv, nullptr, Nimg, T, heads, p, s);
+  p.T = T; p.heads = heads; p.scale = 0.125f;
+  p.trace = g_trace;
+  p.ntiles = (T + 127) / 128;
+  p.nblk = (T + 63) / 64;
+  p.tail_rows = ((T - (p.nblk - 1) * 64) + 15) & ~15;
+  const int D = heads * 64;
+  CUtensorMap tq, tqt;
+  int rc = cg_make_tensor_map_bf16(&tq, qkv, (long long)Nimg * T, 3LL * D, 3LL * D, 64);
+  if (rc) return rc;
+  rc = cg_make_tensor_map_bf16(&tqt, qkv, (long long)Nimg * T, 3LL * D, 3LL * D, p.tail_rows);
+  if (rc) return rc;
+  const size_t opb = (size_t)((p.nblk - 1) * 64 + p.tail_rows) * 128;
+  const size_t smem = 1024 + 3 * opb + 4 * (size_t)TILE_BYTES + (1536 + 128) * 4 + FBARS_BYTES;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  attn_fwd_tc_kernel<<<dim3(heads, Nimg), AT_THREADS, smem, s>>>(tq, tqt, p);
+  CG_LAUNCH_CHECK();
+  return 0;
 }
 
 // delta[n,h,q] = rowsum(dO * O) must already be in `delta` (attn_delta_kernel, vit_attention.cu)
@@ -525,3 +1185,6 @@ int cg_attention_bwd_tc(const void* qkv, const void* dctx, const float* lse, con
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   return launch_attn_tc<false>(qkv, dctx, Nimg, T, heads, p, s);
 }
+
+// debug only (tools/trace_attn.py): device buffer of 16 * 64 * 8 int64 that CTA (0,0) of the next launches fills with clock64() stamps
+extern "C" void cg_debug_attention_trace(void* buf) { g_trace = reinterpret_cast<long long*>(buf); }
