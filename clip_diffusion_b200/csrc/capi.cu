@@ -1,6 +1,7 @@
 // C-ABI plumbing shared by every entry point: thread-local error text, ABI version, device check,
 // and the small cond_fn tail kernels (sample.py:228-238).
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -89,4 +90,13 @@ extern "C" int cg_any_nan(const float* g, int64_t n, float* flag, void* stream) 
   nanflag_kernel<<<1, 1, 0, s>>>(flag, flag);
   CG_LAUNCH_CHECK();
   return 0;
+}
+
+bool cg_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CG_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
 }

@@ -62,3 +62,28 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 static inline cudaStream_t cg_stream(void* s) { return (cudaStream_t)s; }
+
+// Programmatic dependent launch.  The guidance step is a long chain of short dependent kernels (per ViT layer: 9 GEMMs, 3 attention
+// kernels, 4 LayerNorms; many run 10-40 us), so launch latency and kernel prologues (barrier init, TMEM allocation, descriptor
+// prefetch) are a visible share of the step.  Kernels launched through cg_launch_pdl() carry
+// cudaLaunchAttributeProgrammaticStreamSerialization: the grid may start while its predecessor in the stream is still draining; it
+// runs its prologue and then blocks in cg_griddep_wait() until the predecessor has completed and its writes are visible.  Every
+// such kernel calls cg_griddep_launch() at its top (the dependent is scheduled once ALL CTAs of this grid have started) and
+// cg_griddep_wait() in every thread before its first global-memory access.  CG_PDL=0 falls back to plain stream order.
+__device__ __forceinline__ void cg_griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void cg_griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool cg_pdl_enabled();  // capi.cu
+template <typename... KArgs, typename... Args>
+cudaError_t cg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cg_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

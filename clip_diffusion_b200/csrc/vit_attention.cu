@@ -210,6 +210,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) attn_fwd_kernel(const __nv_bfl
 // delta[n,h,q] = sum_d dO[q,d] * O[q,d]; one warp per (n, q), all heads
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx, int T,
                                                          int heads, long long rows, float* __restrict__ delta) {
+  cg_griddep_launch();
+  cg_griddep_wait();
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -455,9 +457,8 @@ extern "C" int cg_attention_bwd(const void* qkv, const void* ctx, const void* dc
   CG_REQUIRE(Tp <= 640, "cg_attention_bwd: T=%d exceeds the shared-memory resident limit (640)", T);
   cudaStream_t s = cg_stream(stream);
   const long long rows = (long long)Nimg * T;
-  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(ctx), reinterpret_cast<const __nv_bfloat16*>(dctx), T, heads,
-                                                               rows, delta_ws);
-  CG_LAUNCH_CHECK();
+  CG_CUDA(cg_launch_pdl(attn_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(ctx),
+                        reinterpret_cast<const __nv_bfloat16*>(dctx), T, heads, rows, delta_ws));
   {
     const int rc_tc = cg_attention_bwd_tc(qkv, dctx, lse, delta_ws, Nimg, T, heads, dqkv, s);
     if (rc_tc != 1) return rc_tc;

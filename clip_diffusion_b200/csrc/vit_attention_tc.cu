@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKVtail, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmDOtail, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  cg_griddep_launch();
   constexpr int NOPS = FWD ? 3 : 4;
   constexpr int NSB = Depth<FWD>::NSB, NPB = Depth<FWD>::NPB;
   constexpr uint32_t STAGE_BYTES = FWD ? TILE_BYTES : 2 * TILE_BYTES;  // backward phase B stages P^T and dS^T
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     for (int o = 0; o < 4; ++o)
       for (int k = 0; k < MAX_BLK; ++k) mbar_init(bars.op(o, k), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    cg_griddep_wait();  // the loads below read the predecessor's output
     // ================= TMA producer: every operand block once, in the order the MMA issuers need them; issued before the CTA-wide
     // sync below (only this thread has touched the barriers so far) so the loads overlap the TMEM allocation
     auto load = [&](int o, int blk) {
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  cg_griddep_wait();
   if (!FWD) {
     // per-query constants of phase B (lane = key, column = query): -lse * log2(e) (-inf beyond T => P = 0 there) and delta
     const float* lb = p.lse + ((long long)n * p.heads + h) * T;
@@ -743,6 +746,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __global__ void __launch_bounds__(AT_THREADS, 1)
     attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKVtail, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  cg_griddep_launch();
   const int T = p.T, D = p.heads * 64;
   const int h = blockIdx.x, n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -771,6 +775,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     for (int o = 0; o < 3; ++o)
       for (int k = 0; k < MAX_BLK; ++k) mbar_init(bars.op(o, k), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    cg_griddep_wait();  // the loads below read the predecessor's output
     auto load = [&](int o, int blk) {
       const bool tail = blk == nblk - 1;
       const uint32_t bar = bars.op(o, blk);
@@ -788,6 +793,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  cg_griddep_wait();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -1140,8 +1146,7 @@ int launch_attn_tc(const void* qkv, const void* dctx, int Nimg, int T, int heads
     CG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  attn_tc_kernel<FWD><<<dim3(heads, Nimg), AT_THREADS, smem, s>>>(tq, tqt, td, tdt, p);
-  CG_LAUNCH_CHECK();
+  CG_CUDA(cg_launch_pdl(attn_tc_kernel<FWD>, dim3(heads, Nimg), dim3(AT_THREADS), smem, s, tq, tqt, td, tdt, p));
   return 0;
 }
 
@@ -1171,8 +1176,7 @@ int cg_attention_fwd_tc(const void* qkv, int Nimg, int T, int heads, void* ctx, 
     CG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  attn_fwd_tc_kernel<<<dim3(heads, Nimg), AT_THREADS, smem, s>>>(tq, tqt, p);
-  CG_LAUNCH_CHECK();
+  CG_CUDA(cg_launch_pdl(attn_fwd_tc_kernel, dim3(heads, Nimg), dim3(AT_THREADS), smem, s, tq, tqt, p));
   return 0;
 }
 

@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tn_kernel(const __gr
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
 
+  cg_griddep_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / BN;
   const int num_tiles = m_tiles * n_tiles;
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tn_kernel(const __gr
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  cg_griddep_wait();  // prologue done: from here on the predecessor's output is read (and buffers it may still read are written)
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -362,6 +364,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES2 + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES2 + 4);
 
+  cg_griddep_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -383,6 +386,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  cg_griddep_wait();
   tcgen05_fence_before();
   cluster_sync_all();
   tcgen05_fence_after();
@@ -556,8 +560,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cuda
   }
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tn_kernel<BN, EPI><<<grid, NUM_THREADS, smem, s>>>(ta, tb, g);
-  CG_LAUNCH_CHECK();
+  CG_CUDA(cg_launch_pdl(gemm_bf16_tn_kernel<BN, EPI>, dim3(grid), dim3(NUM_THREADS), smem, s, ta, tb, g));
   return 0;
 }
 
@@ -587,8 +590,7 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN2);
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm_bf16_tn_pair_kernel<EPI><<<2 * clusters, NUM_THREADS, smem, s>>>(ta, tb, g);
-  CG_LAUNCH_CHECK();
+  CG_CUDA(cg_launch_pdl(gemm_bf16_tn_pair_kernel<EPI>, dim3(2 * clusters), dim3(NUM_THREADS), smem, s, ta, tb, g));
   return 0;
 }
 
@@ -606,26 +608,39 @@ int dispatch_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const G
   return CG_EINVAL;
 }
 
-// CTA-pair kernel selection.  CG_GEMM_PAIR=0 never, =1 whenever eligible, unset = heuristic from the B200 measurements in
-// profiles/ (ViT-L/14 x 64: pair is +16% on K=4096 fp32-out GEMMs, +3..7% on bias/bf16 epilogues, -2% on the QuickGELU
-// epilogues which are epilogue-bound; and 256x256 tiles lose when they quantise badly, e.g. 75 tiles on 74 clusters).
-int pair_mode() {
-  static int v = -2;
-  if (v == -2) {
-    const char* e = getenv("CG_GEMM_PAIR");
-    v = e ? (atoi(e) != 0 ? 1 : 0) : -1;
-  }
-  return v;
+// (pair kernel, ViT-L/14 x 64: +16% on K=4096 fp32-out GEMMs, +3..7% on bias/bf16 epilogues, -2% on the QuickGELU epilogues which
+// are epilogue-bound; 256x256 tiles lose when they quantise badly, e.g. 75 tiles on 74 clusters)
+// Tile shape per problem.  The kernels are persistent (one CTA or CTA pair per SM walks the tile list), so the cost of a shape is
+// waves x columns-per-tile: ceil(tiles / slots) x BN, with the measured per-shape efficiency (B200, tools/bench_gemm_shapes.py ->
+// profiles/r02_gemm_tile_selection.txt):
+//   128 x 256 single CTA   the default: L2 -> smem bound at ~1.0-1.15 PFLOP/s
+//   128 x 128 single CTA   half the columns per tile => half the quantisation step (M = 6304, N = 768: 150 tiles = 2 waves of 256
+//                          columns become 300 tiles = 3 waves of 128; M = 2056 per rank at 8-way strong scaling: 68 -> 136 tiles on
+//                          148 SMs), but each CTA re-reads the A tile for half the work: ~0.85 of the 256-column efficiency
+//   256 x 256 CTA pair     each CTA stages half of B: lifts the L2 bound when K is long (>= 1024) and the epilogue is cheap
+// CG_GEMM_PAIR=0/1 and CG_GEMM_BN=128/256 force a variant (A/B measurements).
+int env_choice(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : -1;
 }
-bool use_pair_kernel(int M, int N, int K, int epilogue) {
-  const int mode = pair_mode();
-  if (mode >= 0) return mode == 1;
-  if (epilogue == CG_EPI_BIAS_QGELU_BF16 || epilogue == CG_EPI_DQGELU_BF16 || K < 1024) return false;
+enum { TILE_256 = 0, TILE_128 = 1, TILE_PAIR = 2 };
+int choose_tile(int M, int N, int K, int epilogue) {
+  static const int force_pair = env_choice("CG_GEMM_PAIR"), force_bn = env_choice("CG_GEMM_BN");
+  const bool can256 = N % 256 == 0;
+  const bool can_pair = can256 && M > 2 * BM;
+  if (!can256 || force_bn == 128) return TILE_128;
+  if (force_pair == 1 && can_pair) return TILE_PAIR;
   const int sms = num_sms();
-  const long long t1 = (long long)((M + BM - 1) / BM) * (N / 256), t2 = (long long)((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
-  const double eff1 = (double)t1 / (double)(((t1 + sms - 1) / sms) * sms);
-  const double eff2 = (double)t2 / (double)(((t2 + sms / 2 - 1) / (sms / 2)) * (sms / 2));
-  return eff2 * 1.10 > eff1;
+  const long long mt = (M + BM - 1) / BM, mt2 = (M + 2 * BM - 1) / (2 * BM);
+  auto waves = [](long long tiles, long long slots) { return (double)((tiles + slots - 1) / slots); };
+  const double c256 = waves(mt * (N / 256), sms) * 256.0;
+  const double c128 = waves(mt * (N / 128), sms) * 128.0 / (K > 1024 ? 0.75 : 0.85);  // the A tile is re-read for half the work: worse with long K
+  const bool heavy_epi = epilogue == CG_EPI_BIAS_QGELU_BF16 || epilogue == CG_EPI_DQGELU_BF16;
+  // a pair tile is two CTAs' worth of rows: per-SM cost = waves x 256 columns, ~10 % faster per tile when K is long
+  const double cpair = (can_pair && force_pair != 0 && !heavy_epi && K >= 1024) ? waves(mt2 * (N / BN2), sms / 2) * 256.0 / (K >= 2048 ? 1.10 : 1.02) : 1e30;
+  if (force_bn == 256) return cpair < c256 ? TILE_PAIR : TILE_256;
+  if (cpair <= c256 && cpair <= c128) return TILE_PAIR;
+  return c128 < c256 ? TILE_128 : TILE_256;
 }
 
 }  // namespace
@@ -657,16 +672,17 @@ extern "C" int cg_gemm_bf16_tn(const void* A, const void* B, int M, int N, int K
                     (!aux || (((uintptr_t)aux & 31) == 0 && aux_row_bytes % 32 == 0)))
                        ? 1
                        : 0;
-  const int bn = (N % 256 == 0) ? 256 : 128;
+  const int tile = choose_tile(M, N, K, epilogue);
   CUtensorMap ta, tb;
   int rc = make_tensor_map(&ta, A, M, K, lda, BM);
   if (rc) return rc;
-  if (bn == 256 && M > 2 * BM && use_pair_kernel(M, N, K, epilogue)) {
+  if (tile == TILE_PAIR) {
     rc = make_tensor_map(&tb, B, N, K, ldb, BN2 / 2);
     if (rc) return rc;
     GemmArgs gp = {M, N, K, bias, out, aux, (long long)ldo, pos, g2, wide};
     return dispatch_pair(epilogue, ta, tb, gp, cg_stream(stream));
   }
+  const int bn = tile == TILE_256 ? 256 : 128;
   rc = make_tensor_map(&tb, B, N, K, ldb, bn);
   if (rc) return rc;
   GemmArgs g = {M, N, K, bias, out, aux, (long long)ldo, pos, g2, wide};

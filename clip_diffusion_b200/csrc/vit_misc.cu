@@ -18,6 +18,8 @@ template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      int M, int D, long long row_stride, __nv_bfloat16* __restrict__ yb, float* __restrict__ yf,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  cg_griddep_launch();
+  cg_griddep_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -54,6 +56,8 @@ template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int M, int D,
                                                      long long row_stride, int accumulate, float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb) {
+  cg_griddep_launch();
+  cg_griddep_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -190,7 +194,7 @@ extern "C" int cg_layernorm_fwd(const float* x, const float* gamma, const float*
   CG_REQUIRE(M > 0 && D > 0 && D % 128 == 0 && D / 32 <= LN_MAX_PER_LANE, "cg_layernorm_fwd: D=%d must be a multiple of 128 and <= %d", D, 32 * LN_MAX_PER_LANE);
   CG_REQUIRE(row_stride >= D && row_stride % 4 == 0, "cg_layernorm_fwd: bad row stride");
 #define CG_LN_FWD(NV) \
-  case NV: ln_fwd_kernel<NV><<<rows_grid(M), 256, 0, cg_stream(stream)>>>(x, gamma, beta, M, D, row_stride, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd); break;
+  case NV: CG_CUDA(cg_launch_pdl(ln_fwd_kernel<NV>, dim3(rows_grid(M)), dim3(256), 0, cg_stream(stream), x, gamma, beta, M, D, (long long)row_stride, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd)); break;
   switch (D / 128) {
     CG_LN_FWD(1) CG_LN_FWD(2) CG_LN_FWD(3) CG_LN_FWD(4) CG_LN_FWD(5) CG_LN_FWD(6) CG_LN_FWD(7) CG_LN_FWD(8) CG_LN_FWD(9) CG_LN_FWD(10)
     default: cg_set_error("cg_layernorm_fwd: unsupported D=%d", D); return CG_EINVAL;
@@ -206,7 +210,7 @@ extern "C" int cg_layernorm_bwd(const float* dy, const float* x, const float* ga
   CG_REQUIRE(M > 0 && D > 0 && D % 128 == 0 && D / 32 <= LN_MAX_PER_LANE, "cg_layernorm_bwd: D=%d must be a multiple of 128 and <= %d", D, 32 * LN_MAX_PER_LANE);
   CG_REQUIRE(row_stride >= D && row_stride % 4 == 0, "cg_layernorm_bwd: bad row stride");
 #define CG_LN_BWD(NV) \
-  case NV: ln_bwd_kernel<NV><<<rows_grid(M), 256, 0, cg_stream(stream)>>>(dy, x, gamma, mean, rstd, M, D, row_stride, accumulate, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16)); break;
+  case NV: CG_CUDA(cg_launch_pdl(ln_bwd_kernel<NV>, dim3(rows_grid(M)), dim3(256), 0, cg_stream(stream), dy, x, gamma, mean, rstd, M, D, (long long)row_stride, accumulate, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16))); break;
   switch (D / 128) {
     CG_LN_BWD(1) CG_LN_BWD(2) CG_LN_BWD(3) CG_LN_BWD(4) CG_LN_BWD(5) CG_LN_BWD(6) CG_LN_BWD(7) CG_LN_BWD(8) CG_LN_BWD(9) CG_LN_BWD(10)
     default: cg_set_error("cg_layernorm_bwd: unsupported D=%d", D); return CG_EINVAL;
