@@ -61,6 +61,7 @@ _SIGNATURES = {
     "cg_check_device": (_I, []),
     "cg_tv_loss_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
     "cg_range_loss_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
+    "cg_image_losses_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P]),
     "cg_spherical_dist_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "cg_spherical_dist_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "cg_spherical_loss_fwd_bwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P]),

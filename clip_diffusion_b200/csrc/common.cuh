@@ -63,6 +63,42 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 static inline cudaStream_t cg_stream(void* s) { return (cudaStream_t)s; }
 
+// Deterministic cross-block reductions (loss values, sum of squares of the guidance gradient): every block stores its partial in a
+// library-owned scratch buffer and the LAST block to arrive (atomic ticket -- the only atomic, and order independent) adds the
+// partials in index order.  No float atomicAdd anywhere: values are bit-reproducible run to run.  The scratch is per device and shared
+// by all reductions: like the reference (module globals, one job per process) the library is not re-entrant across streams.
+constexpr int CG_SCRATCH_FLOATS = 1 << 20;  // partials
+constexpr int CG_SCRATCH_COUNTERS = 16;     // one ticket counter per reduction kind
+struct CgScratch {
+  float* partials;
+  unsigned* counters;
+};
+int cg_get_scratch(CgScratch* out);  // capi.cu: lazily allocated (and zeroed) per device
+
+// Sum `v` of every block of the grid over the contiguous block range [first, first + count) -- called by ALL threads of ALL blocks of the
+// grid.  Returns true in the last block to arrive, where `total` then holds the sum over blocks [0, nblocks) split as the caller wants:
+// the caller loops over its ranges with cg_sum_partials().
+__device__ __forceinline__ bool cg_last_block(float v, float* partials, unsigned* counter, unsigned block_linear, unsigned nblocks) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    partials[block_linear] = v;
+    __threadfence();
+    const unsigned ticket = atomicAdd(counter, 1u);
+    is_last = ticket == nblocks - 1;
+    if (is_last) *counter = 0;  // ready for the next launch
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+// fixed-order sum of partials[first .. first+count) by one whole block; every thread gets the result.  `red` >= 32 floats of smem.
+__device__ __forceinline__ float cg_sum_partials(const float* partials, unsigned first, unsigned count, float* red) {
+  const unsigned tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  float s = 0.f;
+  for (unsigned i = tid; i < count; i += nt) s += __ldcg(partials + first + i);
+  return block_sum(s, red);
+}
+
 // Programmatic dependent launch.  The guidance step is a long chain of short dependent kernels (per ViT layer: 9 GEMMs, 3 attention
 // kernels, 4 LayerNorms; many run 10-40 us), so launch latency and kernel prologues (barrier init, TMEM allocation, descriptor
 // prefetch) are a visible share of the step.  Kernels launched through cg_launch_pdl() carry

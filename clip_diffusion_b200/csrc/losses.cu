@@ -4,12 +4,24 @@
 
 namespace {
 
+// Deterministic loss values: the blocks of one image are a contiguous range of the linear block index; the last block of the grid adds
+// each image's partials in index order (common.cuh) -- no float atomics.
+__device__ __forceinline__ void per_image_loss(float block_total, float inv, float* loss, const CgScratch& ws, int counter, unsigned block_linear,
+                                               unsigned nblocks, unsigned blocks_per_image, unsigned images, float* red) {
+  if (cg_last_block(block_total, ws.partials, ws.counters + counter, block_linear, nblocks)) {
+    for (unsigned b = 0; b < images; ++b) {
+      const float t = cg_sum_partials(ws.partials, b * blocks_per_image, blocks_per_image, red);
+      if (threadIdx.x == 0) loss[b] = t * inv;
+    }
+  }
+}
+
 // ---- total variation (losses.py:20-28) ---------------------------------------------------------
 // One thread per 4 consecutive pixels of a row.  VEC path (W % 4 == 0, 16-byte aligned): three 128-bit loads (row
 // above / this row / row below) + two scalar halo loads per 4 outputs; neighbours come from L1/L2, HBM sees each pixel once.
 template <bool VEC>
 __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, int C, int H, int W, float gscale,
-                                                 int accumulate, float* __restrict__ loss, float* __restrict__ grad) {
+                                                 int accumulate, float* __restrict__ loss, float* __restrict__ grad, CgScratch ws) {
   __shared__ float red[32];
   const int b = blockIdx.y;
   const int64_t plane = (int64_t)H * W;
@@ -78,17 +90,14 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, in
       }
     }
   }
-  if (loss) {
-    const float t = block_sum(acc, red);
-    if (threadIdx.x == 0) atomicAdd(loss + b, t * inv);
-  }
+  if (loss) per_image_loss(block_sum(acc, red), inv, loss, ws, 1, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, gridDim.x, gridDim.y, red);
 }
 
 // 2-D tiled variant (W % 128 == 0): a block owns a 32-row x 128-column tile of one plane; warp w walks rows w, w+8, ...
 // so the rows above/below a warp's row are the rows its neighbour warps load at the same time (L1 hits) -- the row-major
 // grid-stride kernel above re-read every row three times from L2 and stalled at ~50% of HBM peak.
 __global__ void __launch_bounds__(256) tv_tiled_kernel(const float* __restrict__ x, int C, int H, int W, float gscale, int accumulate,
-                                                       float* __restrict__ loss, float* __restrict__ grad) {
+                                                       float* __restrict__ loss, float* __restrict__ grad, CgScratch ws) {
   __shared__ float red[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int plane_id = blockIdx.z;  // b*C + c
@@ -133,15 +142,15 @@ __global__ void __launch_bounds__(256) tv_tiled_kernel(const float* __restrict__
       *o = w;
     }
   }
-  if (loss) {
-    const float t = block_sum(acc, red);
-    if (threadIdx.x == 0) atomicAdd(loss + b, t * inv);
-  }
+  if (loss)
+    per_image_loss(block_sum(acc, red), inv, loss, ws, 2, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, gridDim.x * gridDim.y * gridDim.z,
+                   gridDim.x * gridDim.y * C, gridDim.z / C, red);
+  (void)b;
 }
 
 // ---- rgb range (losses.py:31-35) -----------------------------------------------------------------
 __global__ void __launch_bounds__(256) range_kernel(const float* __restrict__ x, int64_t per_img, float gscale, int accumulate,
-                                                    float* __restrict__ loss, float* __restrict__ grad) {
+                                                    float* __restrict__ loss, float* __restrict__ grad, CgScratch ws) {
   __shared__ float red[32];
   const int b = blockIdx.y;
   const float* xb = x + b * per_img;
@@ -173,9 +182,81 @@ __global__ void __launch_bounds__(256) range_kernel(const float* __restrict__ x,
     acc += d * d;
     if (gb) gb[i] = (accumulate ? gb[i] : 0.f) + gs * d;
   }
-  if (loss) {
-    const float t = block_sum(acc, red);
-    if (threadIdx.x == 0) atomicAdd(loss + b, t * inv);
+  if (loss) per_image_loss(block_sum(acc, red), inv, loss, ws, 3, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, gridDim.x, gridDim.y, red);
+}
+
+// ---- fused image losses: TV + range value and gradient in ONE pass, plus the NaN flag of the finished guidance gradient -------------
+// (sample.py:217-228: tv_loss * denoise_scale [+ range_loss * range_scale] is differentiated, added to grad_tensor and the sum is tested
+// for NaN.)  W % 128 == 0: a block owns a 32-row x 128-column tile of one plane, like tv_tiled_kernel.  grad (+)= d(tv_scale * TV +
+// range_scale * range)/dx; flag[0] = 1 if any element of the finished grad is NaN (the caller zeroes flag[0..1] is NOT needed: the last
+// block writes it).  loss2 (optional) receives [B][2] = (TV, range) values, deterministic.
+__global__ void __launch_bounds__(256) image_losses_kernel(const float* __restrict__ x, int C, int H, int W, float tv_scale, float range_scale,
+                                                           int accumulate, float* __restrict__ loss2, float* __restrict__ grad, float* __restrict__ flag,
+                                                           CgScratch ws) {
+  __shared__ float red[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int plane_id = blockIdx.z;  // b*C + c
+  const int64_t per_img = (int64_t)C * H * W;
+  const float inv = 1.0f / (float)per_img;
+  const float gt = 2.0f * tv_scale * inv, gr = 2.0f * range_scale * inv;
+  const float* xp = x + (int64_t)plane_id * H * W;
+  float* gp = grad + (int64_t)plane_id * H * W;
+  const int x0 = blockIdx.x * 128 + lane * 4;
+  const int h0 = blockIdx.y * 32;
+  float acc_tv = 0.f, acc_rg = 0.f, bad = 0.f;
+#pragma unroll 1
+  for (int r = warp; r < 32; r += 8) {
+    const int h = h0 + r;
+    if (h >= H) break;
+    const float* row = xp + (int64_t)h * W;
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(row + x0));
+    const float left = x0 > 0 ? __ldg(row + x0 - 1) : 0.f;
+    const float right = x0 + 4 < W ? __ldg(row + x0 + 4) : 0.f;
+    float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = u4;
+    if (h > 0) u4 = __ldg(reinterpret_cast<const float4*>(row - W + x0));
+    if (h + 1 < H) d4 = __ldg(reinterpret_cast<const float4*>(row + W + x0));
+    const float cur[6] = {left, c4.x, c4.y, c4.z, c4.w, right};
+    const float up[4] = {u4.x, u4.y, u4.z, u4.w}, dn[4] = {d4.x, d4.y, d4.z, d4.w};
+    float4* o = reinterpret_cast<float4*>(gp + (int64_t)h * W + x0);
+    float prev[4] = {0.f, 0.f, 0.f, 0.f};
+    if (accumulate) { const float4 p = *o; prev[0] = p.x; prev[1] = p.y; prev[2] = p.z; prev[3] = p.w; }
+    float g[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xx = x0 + i;
+      const float c = cur[i + 1];
+      const float dx = (xx + 1 < W) ? cur[i + 2] - c : 0.f;
+      const float dy = (h + 1 < H) ? dn[i] - c : 0.f;
+      const float dxl = (xx > 0) ? c - cur[i] : 0.f;
+      const float dyu = (h > 0) ? c - up[i] : 0.f;
+      acc_tv += dx * dx + dy * dy;
+      const float d = c - fminf(fmaxf(c, -1.f), 1.f);
+      acc_rg += d * d;
+      g[i] = prev[i] + gt * (dxl + dyu - dx - dy) + gr * d;
+      if (g[i] != g[i]) bad = 1.f;
+    }
+    *o = make_float4(g[0], g[1], g[2], g[3]);
+  }
+  // NaN flag: order independent (any block that saw one stores "bad"); flag[1] is the raw indicator, flag[0] the 0/1 flag of the whole grid
+  const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const float tb = block_sum(bad, red);
+  const float t_tv = block_sum(acc_tv, red), t_rg = block_sum(acc_rg, red);
+  if (threadIdx.x == 0) {
+    ws.partials[nblocks + lin] = t_rg;
+    ws.partials[2 * nblocks + lin] = tb;
+  }
+  if (cg_last_block(t_tv, ws.partials, ws.counters + 4, lin, nblocks)) {
+    const float anybad = cg_sum_partials(ws.partials, 2 * nblocks, nblocks, red);
+    if (threadIdx.x == 0) { flag[0] = anybad > 0.f ? 1.f : 0.f; flag[1] = anybad; }
+    if (loss2) {
+      const unsigned per = gridDim.x * gridDim.y * C, images = gridDim.z / C;
+      for (unsigned b = 0; b < images; ++b) {
+        const float a = cg_sum_partials(ws.partials, b * per, per, red);
+        const float c = cg_sum_partials(ws.partials, nblocks + b * per, per, red);
+        if (threadIdx.x == 0) { loss2[2 * b] = a * inv; loss2[2 * b + 1] = c * inv; }
+      }
+    }
   }
 }
 
@@ -214,7 +295,7 @@ __global__ void __launch_bounds__(128) sph_fwd_kernel(const float* __restrict__ 
 // Optionally accumulates loss = sum g*dist into loss_out (fused form).
 __global__ void __launch_bounds__(128) sph_bwd_kernel(const float* __restrict__ emb, const float* __restrict__ txt,
                                                       const float* __restrict__ gdist, const float* __restrict__ w, float coef,
-                                                      int N, int P, int E, float* __restrict__ demb, float* __restrict__ loss_out) {
+                                                      int N, int P, int E, float* __restrict__ demb, float* __restrict__ loss_out, CgScratch ws) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -254,7 +335,13 @@ __global__ void __launch_bounds__(128) sph_bwd_kernel(const float* __restrict__ 
       }
     }
   }
-  if (loss_out && lane == 0) atomicAdd(loss_out, lsum);
+  if (loss_out && lane == 0) ws.partials[n] = lsum;  // summed in index order by sph_loss_sum_kernel
+}
+
+__global__ void __launch_bounds__(256) sph_loss_sum_kernel(CgScratch ws, int N, float* __restrict__ loss_out) {
+  __shared__ float red[32];
+  const float t = cg_sum_partials(ws.partials, 0, (unsigned)N, red);
+  if (threadIdx.x == 0) loss_out[0] = t;
 }
 
 }  // namespace
@@ -271,17 +358,20 @@ extern "C" int cg_tv_loss_fwd_bwd(const float* x, int B, int C, int H, int W, fl
                                   float* grad, void* stream) {
   CG_REQUIRE(x && B > 0 && C > 0 && H > 0 && W > 0, "cg_tv_loss_fwd_bwd: bad arguments");
   cudaStream_t s = cg_stream(stream);
-  if (loss) CG_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * B, s));
+  CgScratch ws;
+  int rc = cg_get_scratch(&ws);
+  if (rc) return rc;
   const int64_t nvec = (int64_t)C * H * ((W + 3) / 4);
   dim3 grid(grid_for(nvec, 256), B);
   const bool vec = (W % 4 == 0) && (((uintptr_t)x | (uintptr_t)grad) & 15) == 0;
-  if (vec && W % 128 == 0 && (long long)B * C <= 65535) {
-    tv_tiled_kernel<<<dim3(W / 128, (H + 31) / 32, B * C), 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad);
+  const long long tiles = (long long)(W / 128) * ((H + 31) / 32) * B * C;
+  if (vec && W % 128 == 0 && (long long)B * C <= 65535 && tiles <= CG_SCRATCH_FLOATS) {
+    tv_tiled_kernel<<<dim3(W / 128, (H + 31) / 32, B * C), 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad, ws);
     CG_LAUNCH_CHECK();
     return 0;
   }
-  if (vec) tv_kernel<true><<<grid, 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad);
-  else tv_kernel<false><<<grid, 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad);
+  if (vec) tv_kernel<true><<<grid, 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad, ws);
+  else tv_kernel<false><<<grid, 256, 0, s>>>(x, C, H, W, grad_scale, accumulate, loss, grad, ws);
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -293,9 +383,11 @@ extern "C" int cg_range_loss_fwd_bwd(const float* x, int B, int C, int H, int W,
   CG_REQUIRE((per_img & 3) == 0 || B == 1, "cg_range_loss_fwd_bwd: C*H*W must be a multiple of 4 when B > 1");
   CG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)grad & 15) == 0, "cg_range_loss_fwd_bwd: pointers must be 16-byte aligned");
   cudaStream_t s = cg_stream(stream);
-  if (loss) CG_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * B, s));
+  CgScratch ws;
+  int rc = cg_get_scratch(&ws);
+  if (rc) return rc;
   dim3 grid(grid_for(per_img / 4 + 1, 256), B);
-  range_kernel<<<grid, 256, 0, s>>>(x, per_img, grad_scale, accumulate, loss, grad);
+  range_kernel<<<grid, 256, 0, s>>>(x, per_img, grad_scale, accumulate, loss, grad, ws);
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -311,7 +403,7 @@ extern "C" int cg_spherical_dist_fwd(const float* emb, const float* txt, int N, 
 extern "C" int cg_spherical_dist_bwd(const float* emb, const float* txt, const float* gdist, int N, int P, int E, float* demb,
                                      void* stream) {
   CG_REQUIRE(emb && txt && gdist && demb && N > 0 && P > 0 && E > 0, "cg_spherical_dist_bwd: bad arguments");
-  sph_bwd_kernel<<<(N + 3) / 4, 128, 0, cg_stream(stream)>>>(emb, txt, gdist, nullptr, 0.f, N, P, E, demb, nullptr);
+  sph_bwd_kernel<<<(N + 3) / 4, 128, 0, cg_stream(stream)>>>(emb, txt, gdist, nullptr, 0.f, N, P, E, demb, nullptr, CgScratch{});
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -319,7 +411,31 @@ extern "C" int cg_spherical_dist_bwd(const float* emb, const float* txt, const f
 extern "C" int cg_spherical_loss_fwd_bwd(const float* emb, const float* txt, const float* w, int N, int P, int E, float coef,
                                          float* loss_out, float* demb, void* stream) {
   CG_REQUIRE(emb && txt && demb && N > 0 && P > 0 && E > 0, "cg_spherical_loss_fwd_bwd: bad arguments");
-  sph_bwd_kernel<<<(N + 3) / 4, 128, 0, cg_stream(stream)>>>(emb, txt, nullptr, w, coef, N, P, E, demb, loss_out);
+  CgScratch ws = {};
+  if (loss_out) {
+    CG_REQUIRE(N <= CG_SCRATCH_FLOATS, "cg_spherical_loss_fwd_bwd: N=%d too large for the loss value (pass loss_out = NULL)", N);
+    int rc = cg_get_scratch(&ws);
+    if (rc) return rc;
+  }
+  sph_bwd_kernel<<<(N + 3) / 4, 128, 0, cg_stream(stream)>>>(emb, txt, nullptr, w, coef, N, P, E, demb, loss_out, ws);
+  CG_LAUNCH_CHECK();
+  if (loss_out) {  // deterministic value: per-row contributions added in index order
+    sph_loss_sum_kernel<<<1, 256, 0, cg_stream(stream)>>>(ws, N, loss_out);
+    CG_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int cg_image_losses_fwd_bwd(const float* x, int B, int C, int H, int W, float tv_scale, float range_scale, int accumulate,
+                                       float* loss2, float* grad, float* nan_flag, void* stream) {
+  CG_REQUIRE(x && grad && nan_flag && B > 0 && C > 0 && H > 0 && W > 0, "cg_image_losses_fwd_bwd: bad arguments");
+  CG_REQUIRE(W % 128 == 0 && (((uintptr_t)x | (uintptr_t)grad) & 15) == 0, "cg_image_losses_fwd_bwd: W=%d must be a multiple of 128 and the pointers 16-byte aligned (use cg_tv_loss_fwd_bwd / cg_range_loss_fwd_bwd / cg_any_nan otherwise)", W);
+  const long long tiles = (long long)(W / 128) * ((H + 31) / 32) * B * C;
+  CG_REQUIRE((long long)B * C <= 65535 && 3 * tiles <= CG_SCRATCH_FLOATS, "cg_image_losses_fwd_bwd: too many tiles (%lld)", tiles);
+  CgScratch ws;
+  int rc = cg_get_scratch(&ws);
+  if (rc) return rc;
+  image_losses_kernel<<<dim3(W / 128, (H + 31) / 32, B * C), 256, 0, cg_stream(stream)>>>(x, C, H, W, tv_scale, range_scale, accumulate, loss2, grad, nan_flag, ws);
   CG_LAUNCH_CHECK();
   return 0;
 }

@@ -230,26 +230,36 @@ class GuidanceStep:
         current_diffusion_step = 1000 - (original_t + 1)
         grad_tensor = torch.zeros(3, x_in.shape[-2], x_in.shape[-1], device=x.device, dtype=torch.float32)
         self.clip_guidance_grad(x_in, current_diffusion_step, grad_tensor)
-        if self.world_size > 1:
-            torch.distributed.all_reduce(grad_tensor, group=self.group)  # the one collective of the step
         H, W = x_in.shape[-2:]
-        # replicated image-space losses, value+gradient in one pass, accumulated into the same buffer
-        _lib.call("cg_tv_loss_fwd_bwd", _lib.ptr(x_in), 1, 3, H, W, float(cfg.denoise_scale), 1, None, _lib.ptr(grad_tensor))
-        if self.range_scale:
-            _lib.call("cg_range_loss_fwd_bwd", _lib.ptr(x_in), 1, 3, H, W, float(self.range_scale), 1, None, _lib.ptr(grad_tensor))
-        if self.init_image_tensor is not None:
+        if self._scratch is None:
+            self._scratch = torch.zeros(4, device=x.device, dtype=torch.float32)
+        flag, scratch = self._scratch[:2], self._scratch[2:]
+        has_init = self.init_image_tensor is not None
+        # replicated image-space losses (sample.py:217-218), value + gradient in one pass, accumulated into the same buffer.  Every rank adds
+        # 1/world of them BEFORE the reduce, so the one collective of the step delivers the finished d(loss)/d(x_in) (exact for
+        # power-of-two world sizes) and nothing but the NaN test follows it.
+        share = 1.0 / self.world_size
+        fused = W % 128 == 0
+        if fused:  # TV + range + NaN flag of the finished gradient in ONE launch
+            _lib.call("cg_image_losses_fwd_bwd", _lib.ptr(x_in), 1, 3, H, W, float(cfg.denoise_scale) * share, float(self.range_scale) * share, 1, None,
+                      _lib.ptr(grad_tensor), _lib.ptr(flag))
+        else:
+            _lib.call("cg_tv_loss_fwd_bwd", _lib.ptr(x_in), 1, 3, H, W, float(cfg.denoise_scale) * share, 1, None, _lib.ptr(grad_tensor))
+            if self.range_scale:
+                _lib.call("cg_range_loss_fwd_bwd", _lib.ptr(x_in), 1, 3, H, W, float(self.range_scale) * share, 1, None, _lib.ptr(grad_tensor))
+        if has_init:
             with torch.enable_grad():
                 xi = x_in.view(1, *x_in.shape[-3:]).detach().requires_grad_()
                 extra = structural_dissimilarity_loss(xi, self.init_image_tensor).sum() * getattr(cfg, "MS_SSIM_scale", 0)
                 if self.LPIPS_model is not None:
                     extra = extra + LPIPS_loss(self.LPIPS_model, xi, self.init_image_tensor).sum() * getattr(cfg, "LPIPS_scale", 0)
                 (gi,) = torch.autograd.grad(extra, xi)
-            grad_tensor += gi.view_as(grad_tensor)
-        if self._scratch is None:
-            self._scratch = torch.zeros(4, device=x.device, dtype=torch.float32)
-        flag, scratch = self._scratch[:2], self._scratch[2:]
+            grad_tensor += gi.view_as(grad_tensor) * share
+        if self.world_size > 1:
+            torch.distributed.all_reduce(grad_tensor, group=self.group)  # the one collective of the step
         self.last_grad_tensor = grad_tensor
-        _lib.call("cg_any_nan", _lib.ptr(grad_tensor), grad_tensor.numel(), _lib.ptr(flag))
+        if self.world_size > 1 or has_init or not fused:
+            _lib.call("cg_any_nan", _lib.ptr(grad_tensor), grad_tensor.numel(), _lib.ptr(flag))
         (grad,) = torch.autograd.grad(denoised_prediction, x, grad_tensor.view_as(denoised_prediction).to(denoised_prediction.dtype))
         grad = grad.float().contiguous()
         out = torch.empty_like(grad)

@@ -47,6 +47,11 @@ int cg_tv_loss_fwd_bwd(const float* x, int B, int C, int H, int W, float grad_sc
 /* rgb_range_loss, clip_diffusion/losses.py:31-35.  Same calling convention as cg_tv_loss_fwd_bwd. */
 int cg_range_loss_fwd_bwd(const float* x, int B, int C, int H, int W, float grad_scale, int accumulate,
                           float* loss, float* grad, void* stream);
+/* The image-space tail of conditon_function in ONE pass (clip_diffusion/sample.py:217-228): grad (+)= d(tv_scale * TV(x) + range_scale *
+ * range(x))/dx, nan_flag[0] = 1 if the finished grad holds a NaN (what `torch.isnan(grad_tensor).any()` tests; nan_flag has 2 floats),
+ * loss2 (optional) = [B][2] values (TV, range).  Needs W % 128 == 0; values are deterministic (no float atomics). */
+int cg_image_losses_fwd_bwd(const float* x, int B, int C, int H, int W, float tv_scale, float range_scale, int accumulate,
+                            float* loss2, float* grad, float* nan_flag, void* stream);
 
 /* square_spherical_distance_loss, clip_diffusion/losses.py:10-16 (with L2_norm, utils/functional.py:74-76).
  *   emb [N,E], txt [P,E] fp32 (un-normalised).  dist [N,P] = 2*asin(||emb^ - txt^||/2)^2. */

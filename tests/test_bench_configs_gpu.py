@@ -192,7 +192,12 @@ def _nccl_worker(rank, world, port, out_path):
     # every rank must hold the same reduced gradient
     gathered = [torch.empty_like(out) for _ in range(world)]
     dist.all_gather(gathered, out.contiguous())
-    same = all(torch.equal(gathered[0], o) for o in gathered)
+    # identical up to the run-to-run noise of the replicated fp32 UNet VJP (cuDNN algorithms with atomics): the reduced d(loss)/d(x_in)
+    # itself is bit-identical on every rank
+    same = all(((gathered[0] - o).norm() / gathered[0].norm()).item() <= 1e-5 for o in gathered)
+    gt = [torch.empty_like(sharded.last_grad_tensor) for _ in range(world)]
+    dist.all_gather(gt, sharded.last_grad_tensor.contiguous())
+    same = same and all(torch.equal(gt[0], o) for o in gt)
     if rank == 0:
         single = GuidanceStep(diffusion, unet, mine, text, config=cfg, record_source=_records())
         single.current_timestep = ct

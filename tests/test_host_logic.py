@@ -21,7 +21,7 @@ def test_library_exports_every_symbol_in_the_header():
     for name in sorted(declared):
         assert hasattr(lib, name), "libclipguide_b200.so does not export %s" % name
     assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
-    assert _lib.load().cg_abi_version() == 3
+    assert _lib.load().cg_abi_version() == 4
     assert _lib.load()._cg_missing == []
 
 

@@ -110,3 +110,70 @@ def test_make_denoised_function_uses_the_kernel_and_matches_the_torch_path():
     a = f(x)
     b = f(x.double()).float()  # non-fp32 input takes the torch.quantile path
     assert (a - b).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 256, 256), (1, 3, 512, 512), (2, 3, 96, 128), (1, 3, 768, 512)])
+def test_fused_image_losses_match_the_oracle_and_are_deterministic(shape):
+    """cg_image_losses_fwd_bwd: TV + range value and gradient + the NaN flag of the finished gradient in ONE launch
+    (sample.py:217-228), against the oracle's autograd; values / gradients bit-identical run to run (no float atomics)."""
+    from clip_diffusion_b200 import _lib
+
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(H + W)
+    x = (torch.tanh(torch.randn(shape, generator=g)) * 1.2).requires_grad_()
+    tv_scale, rg_scale = 10000.0, 150.0
+    tv, rg = O.total_variational_loss(x), O.rgb_range_loss(x)
+    (gref,) = torch.autograd.grad(tv.sum() * tv_scale + rg.sum() * rg_scale, x)
+    base = torch.randn(shape, generator=g)
+    xc = x.detach().cuda().contiguous()
+    outs = []
+    for rep in range(2):
+        grad = base.cuda().clone()
+        loss2 = torch.full((B, 2), float("nan"), device="cuda")
+        flag = torch.full((2,), 7.0, device="cuda")
+        _lib.call("cg_image_losses_fwd_bwd", _lib.ptr(xc), B, C, H, W, tv_scale, rg_scale, 1, _lib.ptr(loss2), _lib.ptr(grad), _lib.ptr(flag))
+        outs.append((grad.cpu(), loss2.cpu(), flag.cpu()))
+    grad, loss2, flag = outs[0]
+    assert _rel(grad - base, gref) < TOL_GRAD
+    assert torch.allclose(loss2[:, 0], tv.detach(), rtol=1e-5) and torch.allclose(loss2[:, 1], rg.detach(), rtol=1e-5, atol=1e-12)
+    assert flag[0].item() == 0.0
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])  # deterministic
+    # NaN anywhere in the finished gradient raises the flag (the reference's isnan(grad_tensor).any(), sample.py:228)
+    bad = base.clone()
+    bad[0, 1, 5, 7] = float("nan")
+    grad = bad.cuda()
+    flag = torch.zeros(2, device="cuda")
+    _lib.call("cg_image_losses_fwd_bwd", _lib.ptr(xc), B, C, H, W, tv_scale, rg_scale, 1, None, _lib.ptr(grad), _lib.ptr(flag))
+    assert flag[0].item() == 1.0
+    # accumulate = 0 overwrites
+    grad = torch.full(shape, float("nan"), device="cuda")
+    _lib.call("cg_image_losses_fwd_bwd", _lib.ptr(xc), B, C, H, W, tv_scale, rg_scale, 0, None, _lib.ptr(grad), _lib.ptr(flag))
+    assert _rel(grad.cpu(), gref) < TOL_GRAD and flag[0].item() == 0.0
+
+
+def test_loss_values_and_clamp_factor_are_bit_reproducible():
+    """loss values and the RMS of the guidance gradient were summed with float atomicAdd.  Now: per-block partials added in
+    index order by the last block."""
+    from clip_diffusion_b200 import _lib
+
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 3, 512, 512, generator=g).cuda()
+    vals = []
+    for rep in range(3):
+        loss = torch.empty(1, device="cuda")
+        grad = torch.empty_like(x)
+        _lib.call("cg_tv_loss_fwd_bwd", _lib.ptr(x), 1, 3, 512, 512, 1.0, 0, _lib.ptr(loss), _lib.ptr(grad))
+        lr = torch.empty(1, device="cuda")
+        _lib.call("cg_range_loss_fwd_bwd", _lib.ptr(x), 1, 3, 512, 512, 1.0, 0, _lib.ptr(lr), _lib.ptr(grad))
+        out = torch.empty_like(x)
+        scratch = torch.zeros(2, device="cuda")
+        _lib.call("cg_grad_finalize", _lib.ptr(x), x.numel(), -1.0, 0.05, None, _lib.ptr(out), _lib.ptr(scratch))
+        emb = torch.randn(64, 768, generator=torch.Generator().manual_seed(2)).cuda()
+        txt = torch.randn(1, 768, generator=torch.Generator().manual_seed(3)).cuda()
+        ls = torch.empty(1, device="cuda")
+        demb = torch.empty_like(emb)
+        _lib.call("cg_spherical_loss_fwd_bwd", _lib.ptr(emb), _lib.ptr(txt), None, 64, 1, 768, 2.0, _lib.ptr(ls), _lib.ptr(demb))
+        vals.append((loss.item(), lr.item(), scratch[0].item(), ls.item(), out.cpu()))
+    for v in vals[1:]:
+        assert v[:4] == vals[0][:4] and torch.equal(v[4], vals[0][4])
+    assert abs(vals[0][2] - float((x.double() ** 2).sum())) / vals[0][2] < 1e-5
