@@ -47,6 +47,10 @@ class CgAug(C.Structure):
         ("cut_index0", C.c_uint64),
         ("noise_std", C.c_float),
         ("input01", C.c_int32),
+        ("noise_mode", C.c_int32),
+        ("noise_threads", C.c_uint32),
+        ("noise_offset", C.c_uint64 * 3),
+        ("noise_total", C.c_uint64),
     ]
 
 
@@ -61,6 +65,8 @@ _SIGNATURES = {
     "cg_check_device": (_I, []),
     "cg_tv_loss_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
     "cg_range_loss_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
+    "cg_randn_like_torch_geometry": (C.c_uint32, [_L, C.POINTER(C.c_uint64)]),
+    "cg_randn_like_torch": (_I, [_P, _L, C.c_uint64, C.c_uint64, _P]),
     "cg_image_losses_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P]),
     "cg_spherical_dist_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "cg_spherical_dist_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),

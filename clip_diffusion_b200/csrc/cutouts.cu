@@ -15,10 +15,12 @@
 
 namespace {
 
-constexpr int TAPS_MAX = 20;  // ceil(4*size/cs): 1024 -> 224 needs 19
-constexpr int TT = 6;         // outputs touching one source pixel: <= ceil(4 + scale) + 1
+constexpr int TAPS_MAX = 32;  // taps per output = ceil(4*size/cs): downscales up to 8x (1792 -> 224, 2048 -> 336 ...)
+constexpr int TT = 24;        // ELL row width of the transposed table: outputs touching one source pixel <= ceil(4 * max(cs/size, 1)) + 2
+                              // (6 when downsampling; an image SMALLER than the cut size is upsampled -- min_size = min(W, H, cut_size),
+                              // cutouts.py:52,84-86 -- up to 336/64 = 5.25x for the sizes Config.update allows)
 constexpr int RT = 8;         // output rows per resample CTA
-constexpr int MAX_SIZE = 1024;
+constexpr int MAX_SIZE = 2048;
 constexpr float GW0 = 0.2989f, GW1 = 0.587f, GW2 = 0.114f;  // torchvision rgb_to_grayscale
 
 struct WsLayout {
@@ -59,6 +61,7 @@ WsLayout ws_layout(int N, int cs, int max_size) {
 
 struct WsHeader {
   int magic, N, cs, max_size, H, W, U, input01;  // U = number of unique crop geometries
+  int tt;                                        // ELL entries in use (6 when every crop is downsampled)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -156,8 +159,8 @@ __global__ void __launch_bounds__(256) tables_kernel(const cg_cut_t* __restrict_
 __global__ void __launch_bounds__(256) resample_fwd_kernel(const float* __restrict__ x_in, int H, int W,
                                                            const cg_cut_t* __restrict__ cuts, int U, const int* __restrict__ tapsN,
                                                            const int* __restrict__ left, const float* __restrict__ wfw, int cs,
-                                                           int input01, float* __restrict__ base) {
-  __shared__ float tmp[RT][MAX_SIZE];
+                                                           int input01, int tmp_ld, float* __restrict__ base) {
+  extern __shared__ float tmp_dyn[];  // [RT][tmp_ld]: the vertically resampled rows of this CTA (tmp_ld = largest crop size of the call)
   __shared__ float s_w[RT][TAPS_MAX];
   __shared__ int s_l[RT];
   const float ka = input01 ? 0.f : 1.f, km = input01 ? 1.f : 0.5f;  // (x + ka) * km
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(256) resample_fwd_kernel(const float* __restri
         }
       }
 #pragma unroll
-      for (int r = 0; r < RT; ++r) tmp[r][lx] = acc[r];
+      for (int r = 0; r < RT; ++r) tmp_dyn[r * tmp_ld + lx] = acc[r];
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < RT * cs; idx += blockDim.x) {
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(256) resample_fwd_kernel(const float* __restri
       float acc = 0.f;
       for (int t = 0; t < taps; ++t) {
         const int lx = lx0 + t;
-        if (lx >= 0 && lx < size) acc = fmaf(w[t], tmp[r][lx], acc);
+        if (lx >= 0 && lx < size) acc = fmaf(w[t], tmp_dyn[r * tmp_ld + lx], acc);
       }
       const int oxs = hflip ? cs - 1 - ox : ox;
       const size_t o = (size_t)oy * cs + oxs;
@@ -272,13 +275,48 @@ struct NoiseSrc {
   uint64_t seed, cut0;
   int N, cs;
   float std;
+  int mode;            // 1: torch's CUDA randn stream (cg_aug_t.noise_mode)
+  uint32_t nthreads;   // grid * 256 of torch's launch for the [N_total,3,cs,cs] tensor
+  uint64_t offset[3];  // generator offset at each of the three randn_like calls
 };
+
+// Element `li` of torch.randn on CUDA (float32): ATen's distribution_nullary_kernel gives thread idx = li % nthreads its k-th
+// curand_normal4 call for li / nthreads = 4 k + ii; curand_init(seed, subsequence = idx, offset) puts offset / 4 (+ k per call) in the
+// low and idx in the high half of the 128-bit Philox counter; curand_normal4 = two Box-Muller pairs (x = s sin, y = s cos).
+__device__ __forceinline__ float torch_randn_elem(uint64_t seed, uint64_t offset, uint32_t nthreads, uint64_t li) {
+  const uint64_t q = li / nthreads;
+  const uint32_t idx = (uint32_t)(li - q * nthreads);
+  const uint64_t c = (offset >> 2) + (q >> 2);
+  const int ii = (int)(q & 3);
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), idx, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const unsigned int xx = ii < 2 ? r.x : r.z, yy = ii < 2 ? r.y : r.w;
+  // _curand_box_muller (curand_normal.h), same expressions so that the compiler contracts them the same way
+  const float CURAND_2POW32_INV_ = 2.3283064e-10f, CURAND_2POW32_INV_2PI_ = 2.3283064e-10f * 6.2831855f;
+  const float u = xx * CURAND_2POW32_INV_ + (CURAND_2POW32_INV_ / 2);
+  const float v = yy * CURAND_2POW32_INV_2PI_ + (CURAND_2POW32_INV_2PI_ / 2);
+  const float s = sqrtf(-2.0f * logf(u));
+  float sn, cs;
+  __sincosf(v, &sn, &cs);
+  return (ii & 1) ? s * cs : s * sn;
+}
+
+__global__ void __launch_bounds__(256) randn_like_torch_kernel(float* __restrict__ out, int64_t numel, uint64_t seed, uint64_t offset, uint32_t nthreads) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = torch_randn_elem(seed, offset, nthreads, (uint64_t)i);
+}
 
 __device__ __forceinline__ void noise3(const NoiseSrc& ns, int stage, int n, int y, int x, float out[3]) {
   const size_t pp = (size_t)ns.cs * ns.cs;
   if (ns.ptr) {
     const float* p = ns.ptr + ((size_t)stage * ns.N + n) * 3 * pp + (size_t)y * ns.cs + x;
     out[0] = ns.std * p[0]; out[1] = ns.std * p[pp]; out[2] = ns.std * p[2 * pp];
+    return;
+  }
+  if (ns.mode == 1) {
+    const uint64_t li = (ns.cut0 + (uint64_t)n) * 3 * pp + (uint64_t)y * ns.cs + x;  // element (n, 0, y, x) of the whole [N_total,3,cs,cs] batch
+    out[0] = ns.std * torch_randn_elem(ns.seed, ns.offset[stage], ns.nthreads, li);
+    out[1] = ns.std * torch_randn_elem(ns.seed, ns.offset[stage], ns.nthreads, li + pp);
+    out[2] = ns.std * torch_randn_elem(ns.seed, ns.offset[stage], ns.nthreads, li + 2 * pp);
     return;
   }
   const uint64_t e = (ns.cut0 + (uint64_t)n) * pp + (uint64_t)y * ns.cs + x;
@@ -771,6 +809,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict
 
 // B3: transposed resample, gather over SOURCE pixels.  grid (ceil(W/32), ceil(H/8)), block (32, 8).
 // Every thread owns one pixel of d(x_in) (3 channels) and loops over the cutouts covering it.
+template <int TTN>
 __global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restrict__ dbase, const cg_cut_t* __restrict__ cuts, const int* __restrict__ hdr,
                                                            const int* __restrict__ tstart, const float* __restrict__ wtr, int cs,
                                                            int max_size, int H, int W, float coef, int accumulate,
@@ -789,19 +828,19 @@ __global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restri
     const int* ts = tstart + (size_t)n * max_size;
     const float* wt = wtr + (size_t)n * max_size * TT;
     const int oy0 = ts[ly], ox0 = ts[lx];
-    float wy[TT], wx[TT];
+    float wy[TTN], wx[TTN];
 #pragma unroll
-    for (int j = 0; j < TT; ++j) { wy[j] = wt[(size_t)ly * TT + j]; wx[j] = wt[(size_t)lx * TT + j]; }
+    for (int j = 0; j < TTN; ++j) { wy[j] = wt[(size_t)ly * TT + j]; wx[j] = wt[(size_t)lx * TT + j]; }
     const float* dn = dbase + (size_t)n * 3 * pp;
     const bool hflip = cut.flags & CG_CUT_HFLIP;
     float a[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int jy = 0; jy < TT; ++jy) {
+    for (int jy = 0; jy < TTN; ++jy) {
       const int oy = oy0 + jy;
       if (wy[jy] == 0.f || oy >= cs) continue;
       float r[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int jx = 0; jx < TT; ++jx) {
+      for (int jx = 0; jx < TTN; ++jx) {
         const int ox = ox0 + jx;
         if (wx[jx] == 0.f || ox >= cs) continue;
         const size_t o = (size_t)oy * cs + (hflip ? cs - 1 - ox : ox);
@@ -825,6 +864,22 @@ __global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restri
 
 }  // namespace
 
+// tt of the latest forward per workspace (the backward entry point does not see the host structs)
+struct TtEntry { const void* ws; int tt; };
+static TtEntry g_tt_cache[64] = {};
+static int g_tt_next = 0;
+static void remember_tt(const void* ws, int tt) {
+  for (auto& e : g_tt_cache)
+    if (e.ws == ws) { e.tt = tt; return; }
+  g_tt_cache[g_tt_next] = {ws, tt};
+  g_tt_next = (g_tt_next + 1) % 64;
+}
+static int recall_tt(const void* ws) {
+  for (auto& e : g_tt_cache)
+    if (e.ws == ws) return e.tt;
+  return TT;  // unknown workspace: the widest (always correct) variant
+}
+
 extern "C" size_t cg_cutouts_workspace_bytes(int N, int cs, int max_size) {
   if (N <= 0 || cs <= 0 || max_size <= 0) return 0;
   return ws_layout(N, cs, max_size).total;
@@ -837,13 +892,21 @@ extern "C" int cg_cutouts_fwd(const float* x_in, int H, int W, const cg_cut_t* c
   CG_REQUIRE(fmt == CG_FMT_F32_NCHW || fmt == CG_FMT_BF16_PATCH, "cg_cutouts_fwd: unknown format %d", fmt);
   if (fmt == CG_FMT_BF16_PATCH)
     CG_REQUIRE(patch > 0 && cs % patch == 0 && kpad >= 3 * patch * patch, "cg_cutouts_fwd: bad patch layout (cs=%d patch=%d kpad=%d)", cs, patch, kpad);
-  int max_size = 0;
+  int max_size = 0, min_sz = 1 << 30;
   for (int i = 0; i < N; ++i) {
-    CG_REQUIRE(cuts_h[i].size >= cs && cuts_h[i].size <= MAX_SIZE, "cg_cutouts_fwd: cut %d size %d outside [%d, %d] (the path only downsamples)", i,
-               cuts_h[i].size, cs, MAX_SIZE);
-    if (cuts_h[i].size > max_size) max_size = cuts_h[i].size;
+    const cg_cut_t& c = cuts_h[i];
+    CG_REQUIRE(c.size >= 1 && c.size <= MAX_SIZE, "cg_cutouts_fwd: cut %d size %d outside [1, %d]", i, c.size, MAX_SIZE);
+    // inner cuts lie inside the image (cutouts.py:84-92 draws x in [0, W - size], y in [0, H - size]); only the overview cut is padded
+    CG_REQUIRE((c.flags & CG_CUT_OVERVIEW) || (c.x0 >= 0 && c.y0 >= 0 && c.x0 + c.size <= W && c.y0 + c.size <= H),
+               "cg_cutouts_fwd: inner cut %d (y0=%d x0=%d size=%d) leaves the %dx%d image", i, c.y0, c.x0, c.size, H, W);
+    if (c.size > max_size) max_size = c.size;
+    if (c.size < min_sz) min_sz = c.size;
   }
-  CG_REQUIRE((max_size * 4 + cs - 1) / cs <= TAPS_MAX, "cg_cutouts_fwd: downscale ratio too large (size %d -> %d)", max_size, cs);
+  CG_REQUIRE((max_size * 4 + cs - 1) / cs <= TAPS_MAX, "cg_cutouts_fwd: downscale ratio above %dx (size %d -> %d)", TAPS_MAX / 4, max_size, cs);
+  // ELL entries needed by the transposed resample: ceil(4 * max(cs / size, 1)) + 2
+  const int tt_need = min_sz >= cs ? 6 : (4 * cs + min_sz - 1) / min_sz + 2;
+  CG_REQUIRE(tt_need <= TT, "cg_cutouts_fwd: upscale ratio too large (size %d -> %d)", min_sz, cs);
+  const int tmp_ld = max_size;
   // the workspace was sized by the caller for max(H,W): use that bound so fwd/bwd agree
   max_size = H > W ? H : W;
   if (max_size > MAX_SIZE) max_size = MAX_SIZE;
@@ -874,8 +937,9 @@ extern "C" int cg_cutouts_fwd(const float* x_in, int H, int W, const cg_cut_t* c
     std::vector<int> fill(cnt.begin(), cnt.end() - 1);
     for (int i = 0; i < N; ++i) duplist_h[fill[uidx_h[i]]++] = i;
   }
-  WsHeader hdr = {0x43475753, N, cs, max_size, H, W, U, aug_h->input01};
+  WsHeader hdr = {0x43475753, N, cs, max_size, H, W, U, aug_h->input01, tt_need <= 6 ? 6 : (tt_need <= 12 ? 12 : 24)};
   memcpy(meta.data(), &hdr, sizeof(hdr));
+  remember_tt(workspace, hdr.tt);
   memcpy(meta.data() + L.cuts, cuts_h, sizeof(cg_cut_t) * N);
   memcpy(meta.data() + L.aug, aug_h, sizeof(cg_aug_t));
   CG_CUDA(cudaMemcpyAsync(ws, meta.data(), L.meta_end, cudaMemcpyHostToDevice, s));  // pageable source: staged before returning
@@ -893,11 +957,21 @@ extern "C" int cg_cutouts_fwd(const float* x_in, int H, int W, const cg_cut_t* c
 
   tables_kernel<<<U, 256, sizeof(int) * cs, s>>>(ucuts, U, cs, max_size, taps, left, wfw, tstart, wtr);
   CG_LAUNCH_CHECK();
-  resample_fwd_kernel<<<dim3((cs + RT - 1) / RT, U), 256, 0, s>>>(x_in, H, W, ucuts, U, taps, left, wfw, cs, aug_h->input01, base);
-  CG_LAUNCH_CHECK();
+  {
+    const size_t tmp_bytes = sizeof(float) * RT * (size_t)tmp_ld;
+    static size_t configured = 48 * 1024;
+    if (tmp_bytes > configured) {
+      CG_CUDA(cudaFuncSetAttribute(resample_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmp_bytes));
+      configured = tmp_bytes;
+    }
+    resample_fwd_kernel<<<dim3((cs + RT - 1) / RT, U), 256, tmp_bytes, s>>>(x_in, H, W, ucuts, U, taps, left, wfw, cs, aug_h->input01, tmp_ld, base);
+    CG_LAUNCH_CHECK();
+  }
   dim3 grid(L.nblk, N);
   if (aug_h->augment) {
-    NoiseSrc ns = {noise, aug_h->noise_seed, aug_h->cut_index0, N, cs, aug_h->noise_std};
+    NoiseSrc ns = {noise, aug_h->noise_seed, aug_h->cut_index0, N, cs, aug_h->noise_std, aug_h->noise_mode, aug_h->noise_threads,
+                   {aug_h->noise_offset[0], aug_h->noise_offset[1], aug_h->noise_offset[2]}};
+    CG_REQUIRE(noise || aug_h->noise_mode != 1 || aug_h->noise_threads > 0, "cg_cutouts_fwd: noise_mode 1 needs noise_threads (cg_randn_like_torch_geometry)");
     augment_fwd_kernel<<<grid, 256, 0, s>>>(base, uidx, aug, ns, cs, z, partial);
     CG_LAUNCH_CHECK();
   }
@@ -936,8 +1010,39 @@ extern "C" int cg_cutouts_bwd(const void* dout, int H, int W, int N, int cs, int
   CG_LAUNCH_CHECK();
   affine_bwd_kernel<<<grid, 256, 0, s>>>(scratch, aug, hdr, cs, base);
   CG_LAUNCH_CHECK();
-  resample_bwd_kernel<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, s>>>(base, ucuts, hdr, tstart, wtr, cs, max_size, H, W,
-                                                                              input01 ? coef : 0.5f * coef, accumulate, dx_in);
+  const dim3 rg((W + 31) / 32, (H + 7) / 8), rb(32, 8);
+  const float rcoef = input01 ? coef : 0.5f * coef;
+  const int tt = recall_tt(workspace);
+  if (tt <= 6) resample_bwd_kernel<6><<<rg, rb, 0, s>>>(base, ucuts, hdr, tstart, wtr, cs, max_size, H, W, rcoef, accumulate, dx_in);
+  else if (tt <= 12) resample_bwd_kernel<12><<<rg, rb, 0, s>>>(base, ucuts, hdr, tstart, wtr, cs, max_size, H, W, rcoef, accumulate, dx_in);
+  else resample_bwd_kernel<24><<<rg, rb, 0, s>>>(base, ucuts, hdr, tstart, wtr, cs, max_size, H, W, rcoef, accumulate, dx_in);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+// torch's launch geometry for a nullary distribution kernel over `numel` elements (ATen/native/cuda/DistributionTemplates.h,
+// calc_execution_policy with block size 256 and unroll factor 4)
+extern "C" uint32_t cg_randn_like_torch_geometry(int64_t numel, uint64_t* offset_increment) {
+  if (numel <= 0) { if (offset_increment) *offset_increment = 0; return 0; }
+  int dev = 0, sms = CG_NUM_SMS, max_threads = 2048;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_threads, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+  }
+  uint64_t grid = (uint64_t)((numel + 255) / 256);
+  const uint64_t cap = (uint64_t)sms * (uint64_t)(max_threads / 256);
+  if (grid > cap) grid = cap;
+  if (offset_increment) *offset_increment = ((uint64_t)(numel - 1) / (256ull * grid * 4ull) + 1ull) * 4ull;
+  return (uint32_t)(grid * 256ull);
+}
+
+extern "C" int cg_randn_like_torch(float* out, int64_t numel, uint64_t seed, uint64_t offset, void* stream) {
+  CG_REQUIRE(out && numel > 0, "cg_randn_like_torch: bad arguments");
+  CG_REQUIRE(offset % 4 == 0, "cg_randn_like_torch: torch's Philox offsets are multiples of 4");
+  const uint32_t nthreads = cg_randn_like_torch_geometry(numel, nullptr);
+  int64_t blocks = (numel + 255) / 256;
+  if (blocks > CG_NUM_SMS * 16) blocks = CG_NUM_SMS * 16;
+  randn_like_torch_kernel<<<(unsigned)blocks, 256, 0, cg_stream(stream)>>>(out, numel, seed, offset, nthreads);
   CG_LAUNCH_CHECK();
   return 0;
 }

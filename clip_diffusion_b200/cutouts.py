@@ -18,13 +18,29 @@ from torch import nn
 from clip_diffusion_b200 import _lib
 from clip_diffusion_b200.rng_record import CutoutRecord, draw_cutout_record
 
+__all__ = ["Cutouts", "MakeCutouts", "make_cutouts", "make_cutouts_from_record", "cutouts_forward", "cutouts_backward", "torch_noise_state"]
+
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
+def torch_noise_state(device, num_cuts, cut_size):
+    """What the reference's three ``torch.randn_like(input)`` calls (cutouts.py:34,40,42) do to the CUDA generator of ``device`` for a
+    ``[num_cuts, 3, cut_size, cut_size]`` float32 batch: returns ``(seed, [offset at call 0, 1, 2], launch threads)`` and advances the
+    generator's Philox offset exactly like the three calls would.  The kernels regenerate those tensors element by element
+    (``cg_aug_t.noise_mode = 1``), so on identical seeds the drop-in equals the reference running on CUDA -- not just statistically."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    numel = int(num_cuts) * 3 * int(cut_size) * int(cut_size)
+    inc = C.c_uint64(0)
+    threads = int(_lib.load().cg_randn_like_torch_geometry(numel, C.byref(inc)))
+    off = int(gen.get_offset())
+    offsets = [off, off + inc.value, off + 2 * inc.value]
+    gen.set_offset(off + 3 * inc.value)
+    return int(gen.initial_seed()), offsets, threads
+
+
 def _device_noise_seed(device):
-    """Philox key for the in-kernel noise, taken from (and advancing) the CUDA generator that the
-    reference's ``torch.randn_like`` would have consumed (cutouts.py:34,40,42)."""
+    """Legacy keying (noise_mode 0): a Philox key derived from the CUDA generator's (seed, offset); advances the offset by 4."""
     gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
     seed = gen.initial_seed()
     off = gen.get_offset()
@@ -57,6 +73,12 @@ def pack_record(rec: CutoutRecord, augment=True, normalize=False, input01=False)
         aug.mean[i], aug.stdv[i] = CLIP_MEAN[i], CLIP_STD[i]
     aug.noise_seed = rec.noise_seed & 0xFFFFFFFFFFFFFFFF
     aug.cut_index0 = rec.first_index()
+    if rec.noise_torch is not None:
+        seed, offsets, threads = rec.noise_torch
+        aug.noise_mode, aug.noise_seed, aug.noise_threads = 1, seed & 0xFFFFFFFFFFFFFFFF, threads
+        for i in range(3):
+            aug.noise_offset[i] = offsets[i]
+        aug.noise_total = rec.total_cuts()
     aug.noise_std = 0.01
     aug.input01 = int(input01)
     return cuts, aug
@@ -74,7 +96,7 @@ def cutouts_forward(x, rec, fmt=_lib.CG_FMT_F32_NCHW, patch=0, kpad=0, augment=T
     if n == 0:
         raise ValueError("no cutouts requested (torch.cat of an empty list fails in the reference too, cutouts.py:111)")
     lib = _lib.load()
-    ws_bytes = lib.cg_cutouts_workspace_bytes(n, cs, min(max(H, W), 1024))
+    ws_bytes = lib.cg_cutouts_workspace_bytes(n, cs, min(max(H, W), 2048))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     cuts, aug = pack_record(rec, augment, normalize, input01)
     noise = None
@@ -121,7 +143,7 @@ class _CutoutsFn(torch.autograd.Function):
 def _draw(input, cut_size, num_overview_cuts, num_inner_cuts, inner_cut_size_power, cut_gray_portion):
     height, width = int(input.shape[2]), int(input.shape[3])
     rec = draw_cutout_record(height, width, cut_size, num_overview_cuts, num_inner_cuts, inner_cut_size_power, cut_gray_portion, noise="device")
-    rec.noise_seed = _device_noise_seed(input.device)
+    rec.noise_torch = torch_noise_state(input.device, rec.num_cuts, cut_size)
     return rec
 
 

@@ -61,6 +61,9 @@ class CutoutRecord:
     # explicit noise tensors [N,3,cs,cs] (parity mode) or None (generated in-kernel from noise_seed)
     noise: Optional[List[torch.Tensor]] = None
     noise_seed: int = 0
+    # torch's CUDA randn stream for the three randn_like calls (cutouts.py:34,40,42): (generator seed, [offset at each call], threads of
+    # torch's launch) as returned by cutouts.torch_noise_state(); None = the library's own keying of noise_seed
+    noise_torch: Optional[tuple] = None
 
     @property
     def num_cuts(self) -> int:
@@ -87,7 +90,7 @@ class CutoutRecord:
         r = CutoutRecord(self.height, self.width, self.cut_size, 0, stop - start)
         r.y0, r.x0 = self.y0[start:stop], self.x0[start:stop]
         r.size, r.flags = self.size[start:stop], self.flags[start:stop]
-        for k in ("flip", "angle", "tx", "ty", "gray", "perm", "brightness", "contrast", "saturation", "hue", "noise_seed"):
+        for k in ("flip", "angle", "tx", "ty", "gray", "perm", "brightness", "contrast", "saturation", "hue", "noise_seed", "noise_torch"):
             setattr(r, k, getattr(self, k))
         if self.noise is not None:
             r.noise = [n[start:stop] for n in self.noise]
@@ -96,6 +99,10 @@ class CutoutRecord:
 
     def first_index(self) -> int:
         return getattr(self, "_slice_of", (0, self.num_cuts))[0]
+
+    def total_cuts(self) -> int:
+        """Cutouts of the whole batch this record (or shard) belongs to."""
+        return getattr(self, "_slice_of", (0, self.num_cuts))[1]
 
 
 def draw_cutout_record(

@@ -20,7 +20,7 @@ import torch
 
 from clip_diffusion_b200 import _lib
 from clip_diffusion_b200.config import Config
-from clip_diffusion_b200.cutouts import _device_noise_seed, cutouts_backward, cutouts_forward, make_cutouts
+from clip_diffusion_b200.cutouts import cutouts_backward, cutouts_forward, make_cutouts, torch_noise_state
 from clip_diffusion_b200.losses import (LPIPS_loss, aesthetic_loss, square_spherical_distance_loss, structural_dissimilarity_loss,
                                         total_variational_loss)
 from clip_diffusion_b200.rng_record import draw_cutout_record
@@ -162,7 +162,7 @@ class GuidanceStep:
                     rec = self.record_source(name, b, H, W, tower.input_resolution, n_over, n_inner, power, gray)
                 else:
                     rec = draw_cutout_record(H, W, tower.input_resolution, n_over, n_inner, power, gray, noise="device")
-                    rec.noise_seed = _device_noise_seed(x_in.device)
+                    rec.noise_torch = torch_noise_state(x_in.device, rec.num_cuts, tower.input_resolution)  # the reference's CUDA randn stream
                 self.last_records.append(rec)
                 start, stop = shard_range(n_total, self.rank, self.world_size)
                 if stop <= start:

@@ -96,6 +96,15 @@ typedef struct {
   float noise_std;     /* 0.01 in the reference (cutouts.py:34,40,42) */
   int32_t input01;     /* 1: x_in is already in [0,1] (Cutouts.forward, cutouts.py:47); 0: [-1,1] and the
                           kernel applies denormalize_image_zero_to_one (image_utils.py:40-42) on load */
+  /* In-kernel noise that reproduces the reference ON CUDA bit for bit: the three `torch.randn_like(input)` calls of cutouts.py:34,40,42
+   * draw from torch's CUDA generator (Philox4x32-10, curand_normal4, the thread/element mapping of ATen's distribution_nullary_kernel).
+   * noise_mode 1: noise_seed = the generator's seed, noise_offset[s] = its Philox offset at the s-th call, noise_total = cutouts of
+   * the WHOLE batch (shards generate their slice of the same stream; cut_index0 is the slice start), noise_threads = grid * 256 of
+   * torch's launch for that tensor (cg_randn_like_torch_geometry).  noise_mode 0: the library's own counter-based keying. */
+  int32_t noise_mode;
+  uint32_t noise_threads;
+  uint64_t noise_offset[3];
+  uint64_t noise_total;
 } cg_aug_t;
 
 /* output formats of cg_cutouts_fwd / input format of cg_cutouts_bwd */
@@ -104,6 +113,13 @@ typedef struct {
 #define CG_FMT_F32_PATCH 2  /* same layout in fp32: the conv1 dgrad GEMM's output, accepted by cg_cutouts_bwd as `dout` */
 
 size_t cg_cutouts_workspace_bytes(int N, int cs, int max_size);
+
+/* torch.randn / torch.randn_like for a float32 CUDA tensor of `numel` elements, reproduced from the generator state (seed, Philox offset
+ * at the call): out[i] equals what torch writes, bit for bit (cutouts.py:34,40,42 on a CUDA device).  cg_randn_like_torch_geometry
+ * returns the thread count of torch's launch (grid * 256, host only: device properties) and, through *offset_increment, by how much
+ * the call advances the generator's offset. */
+uint32_t cg_randn_like_torch_geometry(int64_t numel, uint64_t* offset_increment);
+int cg_randn_like_torch(float* out, int64_t numel, uint64_t seed, uint64_t offset, void* stream);
 
 /* make_cutouts, clip_diffusion/cutouts.py:117-134 (+ CLIP_NORMALIZE) as fused kernels.
  *   x_in [3,H,W] fp32 in [-1,1]; cuts_h/aug_h are HOST structs (copied asynchronously);

@@ -33,6 +33,13 @@ CASES = [
     (512, 512, 224, 1, 8, 5, 0.3, 9),
     (512, 512, 224, 3, 8, 5, 0.3, 10),
     (512, 512, 224, 6, 2, 0.5, 1.0, 11),
+    # the reference's min_size = min(W, H, cut_size) branch (cutouts.py:52,84-86): an image SMALLER than the CLIP resolution is upsampled
+    (128, 192, 224, 2, 3, 5, 0.3, 12),
+    (256, 256, 336, 3, 3, 5, 0.3, 13),   # 256^2 image with ViT-L/14@336px
+    (64, 128, 224, 1, 2, 5, 0.3, 14),    # 3.5x upsample of the inner cuts
+    # downscales above 5x and crops above 1024 (Config.update allows any multiple of 64)
+    (1280, 1280, 224, 2, 3, 5, 0.3, 15),
+    (1536, 1024, 224, 1, 2, 1, 0.3, 16),
 ]
 
 
@@ -222,3 +229,60 @@ def test_cutouts_forward_input_in_unit_range():
     xm = x.cuda().requires_grad_()
     (gm1,) = torch.autograd.grad(make_cutouts_from_record(xm, rec, input01=False).sum(), xm)
     assert ((g01 * 0.5 - gm1).norm() / gm1.norm()).item() < 1e-5  # d((x+1)/2)/dx = 1/2
+
+
+def test_inner_cut_outside_the_image_is_rejected():
+    """an out-of-range descriptor passed through the C ABI must be an error, not silent zero padding."""
+    from clip_diffusion_b200 import _lib
+    from clip_diffusion_b200.cutouts import cutouts_forward
+
+    x, rec = _record(CASES[7])
+    rec.x0[0] = 512 - rec.size[0] + 5  # inner cut hanging over the right edge
+    with pytest.raises(_lib.ClipGuideError, match="leaves the"):
+        cutouts_forward(x.cuda(), rec)
+
+
+@pytest.mark.parametrize("numel,skip", [(7, 0), (256, 4), (1000, 8), (3 * 224 * 224, 0), (303104 * 4 + 5, 12), (16 * 3 * 224 * 224, 1024), (64 * 3 * 224 * 224, 40)])
+def test_randn_like_torch_reproduces_torchs_cuda_stream(numel, skip):
+    """the reference draws its three noise tensors with torch.randn_like on the CUDA generator (cutouts.py:34,40,42).
+    cg_randn_like_torch regenerates that stream from (seed, offset): Philox4x32-10, curand_normal4, ATen's thread/element mapping --
+    bit for bit, including the offset increment of the call."""
+    import ctypes
+
+    from clip_diffusion_b200 import _lib
+
+    torch.cuda.manual_seed(1234 + numel)
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    if skip:
+        gen.set_offset(skip)
+    off0 = gen.get_offset()
+    ref = torch.randn(numel, device="cuda")
+    inc = ctypes.c_uint64(0)
+    threads = _lib.load().cg_randn_like_torch_geometry(numel, ctypes.byref(inc))
+    assert gen.get_offset() - off0 == inc.value and threads % 256 == 0
+    out = torch.empty(numel, device="cuda")
+    _lib.call("cg_randn_like_torch", _lib.ptr(out), numel, gen.initial_seed(), off0)
+    same = (out == ref)
+    assert bool(same.all()), "%d of %d elements differ (max abs %g)" % (int((~same).sum()), numel, (out - ref).abs().max().item())
+
+
+def test_dropin_noise_equals_the_reference_on_cuda():
+    """make_cutouts on identical seeds == the reference executed on a CUDA device: crop / augmentation parameters from the CPU generator
+    (bit exact), the three noise tensors from the CUDA generator in call order (regenerated in-kernel)."""
+    from clip_diffusion_b200.cutouts import make_cutouts
+    from clip_diffusion_b200.rng_record import draw_cutout_record
+
+    H, W, cs, no, ni = 256, 320, 224, 3, 6
+    x = torch.tanh(torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(3)))
+    # what the reference does on CUDA, restated with the oracle: CPU draws in order, the noise via torch.randn on the device generator
+    torch.manual_seed(77)
+    torch.cuda.manual_seed(77)
+    rec = draw_cutout_record(H, W, cs, no, ni, 5, 0.3, noise="device")
+    rec.noise = [torch.randn(no + ni, 3, cs, cs, device="cuda").cpu() for _ in range(3)]
+    after_ref = torch.cuda.default_generators[torch.cuda.current_device()].get_offset()
+    ref = OC.make_cutouts(x, rec)
+    torch.manual_seed(77)
+    torch.cuda.manual_seed(77)
+    out = make_cutouts(x.cuda(), cs, no, ni, 5, 0.3)
+    assert torch.cuda.default_generators[torch.cuda.current_device()].get_offset() == after_ref  # the generator advanced identically
+    assert (out.cpu() - ref).abs().max().item() <= PIXEL_TOL

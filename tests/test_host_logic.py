@@ -29,8 +29,9 @@ def test_struct_layouts_match_the_header():
     from clip_diffusion_b200 import _lib
 
     assert ctypes.sizeof(_lib.CgCut) == 16
-    assert ctypes.sizeof(_lib.CgAug) == 144
+    assert ctypes.sizeof(_lib.CgAug) == 184
     assert _lib.CgAug.noise_seed.offset == 120 and _lib.CgAug.input01.offset == 140
+    assert _lib.CgAug.noise_mode.offset == 144 and _lib.CgAug.noise_offset.offset == 152 and _lib.CgAug.noise_total.offset == 176
 
 
 def test_ops_refuse_cpu_tensors_and_bad_arguments_without_a_gpu():

@@ -97,12 +97,14 @@ def test_reference_in_place_losses():
 
 
 # ---- ResizeRight restatement: independent cross-checks (the real package is not available: parity unpinned) -------------
-@pytest.mark.parametrize("size,cs", [(512, 224), (300, 224), (97, 64), (768, 336)])
+@pytest.mark.parametrize("size,cs", [(512, 224), (300, 224), (97, 64), (768, 336), (1280, 224), (128, 224), (256, 336), (64, 224)])
 def test_resize_matches_torch_antialiased_bicubic_in_the_interior(size, cs):
+    """Down- AND up-sampling (the min_size = min(W, H, cut_size) branch of cutouts.py:52 upsamples images smaller than the CLIP
+    resolution): torch's antialiased bicubic uses the same Keys a = -0.5 kernel, stretched only when downsampling."""
     x = torch.rand(1, 3, size, size, generator=torch.Generator().manual_seed(size))
     mine = RR.resize(x, out_shape=[1, 3, cs, cs])
     ref = torch.nn.functional.interpolate(x, size=(cs, cs), mode="bicubic", antialias=True, align_corners=False)
-    m = 4  # borders differ by design: ResizeRight zero-pads and keeps the padded taps in the normalisation
+    m = max(4, int(2 * max(cs / size, 1.0) + 2))  # borders differ by design: ResizeRight zero-pads and keeps the padded taps in the normalisation
     assert (mine[..., m:-m, m:-m] - ref[..., m:-m, m:-m]).abs().max().item() < 5e-5
 
 
