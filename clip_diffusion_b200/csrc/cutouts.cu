@@ -959,7 +959,7 @@ extern "C" int cg_cutouts_fwd(const float* x_in, int H, int W, const cg_cut_t* c
   CG_LAUNCH_CHECK();
   {
     const size_t tmp_bytes = sizeof(float) * RT * (size_t)tmp_ld;
-    static size_t configured = 48 * 1024;
+    static size_t configured = 40 * 1024;  // static shared memory (weights, first taps) shares the 48 KB default limit
     if (tmp_bytes > configured) {
       CG_CUDA(cudaFuncSetAttribute(resample_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmp_bytes));
       configured = tmp_bytes;

@@ -210,9 +210,14 @@ def test_excessive_downscale_is_refused_loudly():
     from clip_diffusion_b200.cutouts import cutouts_forward
     from clip_diffusion_b200.rng_record import draw_cutout_record
 
+    # up to 8x is supported (32 taps): 256 -> 32 runs and matches the oracle; 320 -> 32 is refused with a clear message
     rec = draw_cutout_record(256, 256, 32, 1, 0, 5, 0.3, generator=torch.Generator().manual_seed(0), noise="cpu")
+    x = torch.tanh(torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(1)))
+    out, _ = cutouts_forward(x.cuda(), rec, augment=False)
+    assert (out.cpu() - OC.base_cutouts(x.add(1).div(2), rec)).abs().max().item() <= PIXEL_TOL
+    rec = draw_cutout_record(320, 320, 32, 1, 0, 5, 0.3, generator=torch.Generator().manual_seed(0), noise="cpu")
     with pytest.raises(ClipGuideError, match="downscale ratio"):
-        cutouts_forward(torch.zeros(1, 3, 256, 256, device="cuda"), rec)
+        cutouts_forward(torch.zeros(1, 3, 320, 320, device="cuda"), rec)
 
 
 def test_cutouts_forward_input_in_unit_range():
