@@ -67,6 +67,8 @@ _SIGNATURES = {
     "cg_range_loss_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
     "cg_randn_like_torch_geometry": (C.c_uint32, [_L, C.POINTER(C.c_uint64)]),
     "cg_randn_like_torch": (_I, [_P, _L, C.c_uint64, C.c_uint64, _P]),
+    "cg_ms_ssim_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "cg_ms_ssim_dissimilarity_fwd_bwd": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P]),
     "cg_image_losses_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P]),
     "cg_spherical_dist_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "cg_spherical_dist_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
@@ -104,7 +106,7 @@ _lib = None
 launch_count = 0     # C-ABI calls made through this module
 kernel_launches = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
 # kernels launched per entry point (csrc/*.cu); 1 unless listed
-_KERNELS_PER_CALL = {"cg_cutouts_fwd": 4, "cg_cutouts_bwd": 4, "cg_attention_bwd": 3, "cg_grad_finalize": 2, "cg_any_nan": 2, "cg_dynamic_threshold": 5, "cg_groupnorm_nhwc_fwd": 3, "cg_groupnorm_nhwc_bwd": 3}
+_KERNELS_PER_CALL = {"cg_cutouts_fwd": 4, "cg_cutouts_bwd": 4, "cg_ms_ssim_dissimilarity_fwd_bwd": 17, "cg_attention_bwd": 3, "cg_grad_finalize": 2, "cg_any_nan": 2, "cg_dynamic_threshold": 5, "cg_groupnorm_nhwc_fwd": 3, "cg_groupnorm_nhwc_bwd": 3}
 
 
 class ClipGuideError(RuntimeError):

@@ -109,59 +109,40 @@ def LPIPS_loss(LPIPS_model, input, image):
     return LPIPS_model(input, image)
 
 
-def _gaussian_window(size=11, sigma=1.5, device=None, dtype=torch.float32):
-    coords = torch.arange(size, device=device, dtype=dtype) - size // 2
-    g = torch.exp(-(coords ** 2) / (2 * sigma ** 2))
-    return g / g.sum()
+class _MsSsimFn(torch.autograd.Function):
+    """1 - MS-SSIM(input, image), value and analytic gradient w.r.t. ``input`` from csrc/msssim.cu (the init image is a constant)."""
 
+    @staticmethod
+    def forward(ctx, input, image):
+        _lib.require_cuda(input, image)
+        if input.dim() != 4 or input.shape != image.shape:
+            raise ValueError("expected two [B,C,H,W] images of the same shape, got %s and %s" % (tuple(input.shape), tuple(image.shape)))
+        x, y = _as_f32_contig(input), _as_f32_contig(image)
+        B, C, H, W = x.shape
+        lib = _lib.load()
+        ws_bytes = lib.cg_ms_ssim_workspace_bytes(C, H, W)
+        if ws_bytes == 0:
+            raise _lib.ClipGuideError(lib.cg_last_error().decode("utf-8", "replace") or "MS-SSIM: unsupported image size %dx%d" % (H, W))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        vals = torch.empty(B, device=x.device, dtype=torch.float32)
+        grad = torch.empty_like(x)
+        for b in range(B):  # the guidance path has batch 1 (sample.py:246-251)
+            _lib.call("cg_ms_ssim_dissimilarity_fwd_bwd", _lib.ptr(x[b]), _lib.ptr(y[b]), C, H, W, 1.0, 0, _lib.ptr(vals[b:]), _lib.ptr(grad[b]), _lib.ptr(ws))
+        ctx.save_for_backward(grad)
+        ctx.batch, ctx.in_dtype = B, input.dtype
+        return vals.mean()  # size_average=True: one value for the batch
 
-def _gaussian_filter(x, win):
-    """separable 'valid' gaussian blur, one filter per channel (pytorch_msssim.gaussian_filter)"""
-    c = x.shape[1]
-    k = win.view(1, 1, -1).repeat(c, 1, 1)
-    if x.shape[2] >= win.numel():
-        x = torch.nn.functional.conv2d(x, k.unsqueeze(-1), groups=c)
-    if x.shape[3] >= win.numel():
-        x = torch.nn.functional.conv2d(x, k.unsqueeze(-2), groups=c)
-    return x
-
-
-def ms_ssim(x, y, data_range=1.0, win_size=11, win_sigma=1.5, weights=(0.0448, 0.2856, 0.3001, 0.2363, 0.1333), k1=0.01, k2=0.03):
-    """Multi-scale SSIM as the un-vendored ``pytorch_msssim.MS_SSIM(win_size=11, win_sigma=1.5, data_range=1,
-    size_average=True, channel=3)`` the reference builds at losses.py:7 (restated from the published algorithm: 5 scales,
-    2x2 average pooling between scales, relu on the contrast-structure terms, weighted geometric mean).  Stock torch ops:
-    the init-image branch (sample.py:220-225) is outside the kernel path; parity against the real
-    package is unpinned."""
-    if min(x.shape[-2:]) <= (win_size - 1) * 2 ** 4:
-        raise ValueError("image side must exceed %d for 5-scale MS-SSIM" % ((win_size - 1) * 2 ** 4))
-    win = _gaussian_window(win_size, win_sigma, x.device, x.dtype)
-    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
-    mcs = []
-    for level in range(len(weights)):
-        mu1, mu2 = _gaussian_filter(x, win), _gaussian_filter(y, win)
-        s11 = _gaussian_filter(x * x, win) - mu1 * mu1
-        s22 = _gaussian_filter(y * y, win) - mu2 * mu2
-        s12 = _gaussian_filter(x * y, win) - mu1 * mu2
-        cs_map = (2 * s12 + c2) / (s11 + s22 + c2)
-        ssim_map = ((2 * mu1 * mu2 + c1) / (mu1 * mu1 + mu2 * mu2 + c1)) * cs_map
-        cs = cs_map.flatten(2).mean(-1)
-        if level < len(weights) - 1:
-            mcs.append(torch.relu(cs))
-            pad = [s % 2 for s in x.shape[2:]]
-            x = torch.nn.functional.avg_pool2d(x, kernel_size=2, padding=pad)
-            y = torch.nn.functional.avg_pool2d(y, kernel_size=2, padding=pad)
-        else:
-            mcs.append(torch.relu(ssim_map.flatten(2).mean(-1)))
-    stack = torch.stack(mcs, dim=0)  # [levels, B, C]
-    w = torch.tensor(weights, device=x.device, dtype=x.dtype).view(-1, 1, 1)
-    return torch.prod(stack ** w, dim=0).mean()  # size_average=True
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * (g / ctx.batch)).to(ctx.in_dtype), None
 
 
 def structural_dissimilarity_loss(input, image):
-    """1 - MS-SSIM of the two images mapped to [0,1]   (losses.py:48-54)"""
-    input = (input + 1) / 2
-    image = (image + 1) / 2
-    return 1.0 - ms_ssim(input, image)
+    """1 - MS-SSIM of the two images mapped to [0,1] (losses.py:48-54; ``pytorch_msssim.MS_SSIM(win_size=11, win_sigma=1.5, data_range=1,
+    size_average=True, channel=3)``, losses.py:7) as CUDA kernels with an analytic gradient.  CUDA tensors only (no CPU path); the
+    float64 restatement used to check it lives in oracle/ms_ssim.py."""
+    return _MsSsimFn.apply(input, image)
 
 
 # north_star vocabulary

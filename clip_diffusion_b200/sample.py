@@ -138,6 +138,7 @@ class GuidanceStep:
         self.last_records = []  # RNG records of the latest call, per (model, cutout batch)
         self.cutouts_processed = 0
         self._scratch = None
+        self._ms_ws = None
 
     # ---- the CLIP part: d(sum of CLIP objectives)/d(x_in), local shard only ---------------------------------
     def clip_guidance_grad(self, x_in, current_diffusion_step, grad_out):
@@ -247,14 +248,21 @@ class GuidanceStep:
             _lib.call("cg_tv_loss_fwd_bwd", _lib.ptr(x_in), 1, 3, H, W, float(cfg.denoise_scale) * share, 1, None, _lib.ptr(grad_tensor))
             if self.range_scale:
                 _lib.call("cg_range_loss_fwd_bwd", _lib.ptr(x_in), 1, 3, H, W, float(self.range_scale) * share, 1, None, _lib.ptr(grad_tensor))
-        if has_init:
-            with torch.enable_grad():
-                xi = x_in.view(1, *x_in.shape[-3:]).detach().requires_grad_()
-                extra = structural_dissimilarity_loss(xi, self.init_image_tensor).sum() * getattr(cfg, "MS_SSIM_scale", 0)
-                if self.LPIPS_model is not None:
-                    extra = extra + LPIPS_loss(self.LPIPS_model, xi, self.init_image_tensor).sum() * getattr(cfg, "LPIPS_scale", 0)
-                (gi,) = torch.autograd.grad(extra, xi)
-            grad_tensor += gi.view_as(grad_tensor) * share
+        if has_init:  # sample.py:220-225: MS-SSIM is evaluated whenever an init image exists, even at scale 0 (config.py:52)
+            init = self.init_image_tensor.reshape(3, H, W).float().contiguous()
+            nbytes = _lib.load().cg_ms_ssim_workspace_bytes(3, H, W)
+            if nbytes == 0:
+                raise _lib.ClipGuideError(_lib.load().cg_last_error().decode("utf-8", "replace"))
+            if self._ms_ws is None or self._ms_ws.numel() < nbytes:
+                self._ms_ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _lib.call("cg_ms_ssim_dissimilarity_fwd_bwd", _lib.ptr(x_in), _lib.ptr(init), 3, H, W, float(getattr(cfg, "MS_SSIM_scale", 0)) * share, 1, None,
+                      _lib.ptr(grad_tensor), _lib.ptr(self._ms_ws))
+            if self.LPIPS_model is not None:  # the caller's (un-vendored) VGG LPIPS network: stock PyTorch, outside the kernel path
+                with torch.enable_grad():
+                    xi = x_in.view(1, *x_in.shape[-3:]).detach().requires_grad_()
+                    extra = LPIPS_loss(self.LPIPS_model, xi, self.init_image_tensor).sum() * getattr(cfg, "LPIPS_scale", 0)
+                    (gi,) = torch.autograd.grad(extra, xi)
+                grad_tensor += gi.view_as(grad_tensor) * share
         if self.world_size > 1:
             torch.distributed.all_reduce(grad_tensor, group=self.group)  # the one collective of the step
         self.last_grad_tensor = grad_tensor

@@ -47,6 +47,14 @@ int cg_tv_loss_fwd_bwd(const float* x, int B, int C, int H, int W, float grad_sc
 /* rgb_range_loss, clip_diffusion/losses.py:31-35.  Same calling convention as cg_tv_loss_fwd_bwd. */
 int cg_range_loss_fwd_bwd(const float* x, int B, int C, int H, int W, float grad_scale, int accumulate,
                           float* loss, float* grad, void* stream);
+/* structural_dissimilarity_loss, clip_diffusion/losses.py:48-54 (init-image branch of conditon_function, sample.py:220-225): 1 - MS-SSIM of
+ * x and y, both [C,H,W] fp32 in [-1,1] (mapped to [0,1] inside, image_utils.py:40-42), with pytorch_msssim.MS_SSIM(win_size=11,
+ * win_sigma=1.5, data_range=1, size_average=True) semantics (5 scales; the package itself is not vendored by the reference: restated from
+ * its published algorithm, oracle/ms_ssim.py).  loss (optional) = the value; grad (optional) (+)= grad_scale * d loss / d x.  H, W
+ * multiples of 16, smaller side > 160.  workspace: cg_ms_ssim_workspace_bytes. */
+size_t cg_ms_ssim_workspace_bytes(int C, int H, int W);
+int cg_ms_ssim_dissimilarity_fwd_bwd(const float* x, const float* y, int C, int H, int W, float grad_scale, int accumulate, float* loss,
+                                     float* grad, void* workspace, void* stream);
 /* The image-space tail of conditon_function in ONE pass (clip_diffusion/sample.py:217-228): grad (+)= d(tv_scale * TV(x) + range_scale *
  * range(x))/dx, nan_flag[0] = 1 if the finished grad holds a NaN (what `torch.isnan(grad_tensor).any()` tests; nan_flag has 2 floats),
  * loss2 (optional) = [B][2] values (TV, range).  Needs W % 128 == 0; values are deterministic (no float atomics). */

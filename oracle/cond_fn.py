@@ -5,7 +5,8 @@ oracle.losses / oracle.clip_vit).  Differences, all needed to make it a checker:
   * random decisions come from ``record_source`` (explicit RNG records incl. noise) instead of the global
     generator, so the CUDA path can be fed the identical parameters;
   * ``diffusion`` / ``model`` are arguments (any object with p_mean_variance / sqrt_one_minus_alphas_cumprod);
-  * the init-image branch (sample.py:220-225: LPIPS + MS-SSIM, un-vendored nets) is not restated.
+  * the init-image branch (sample.py:220-225): the MS-SSIM term is restated (oracle/ms_ssim.py, parity unpinned: ``pytorch_msssim`` is
+    not vendored); the LPIPS term needs the un-vendored VGG network and is left out.
 """
 import torch
 
@@ -14,7 +15,7 @@ from oracle import losses as OL
 
 
 def make_conditon_function(diffusion, model, clip_models, text_embeddings_and_weights, get_current_timestep, config, record_source,
-                           aesthetic_predictors=None, range_scale=0.0):
+                           aesthetic_predictors=None, range_scale=0.0, init_image_tensor=None):
     aesthetic_predictors = aesthetic_predictors or {}
 
     @torch.enable_grad()
@@ -52,6 +53,10 @@ def make_conditon_function(diffusion, model, clip_models, text_embeddings_and_we
         loss_sum = OL.total_variational_loss(denoised_prediction).sum() * config.denoise_scale  # :217-218
         if range_scale:
             loss_sum = loss_sum + OL.rgb_range_loss(denoised_prediction).sum() * range_scale
+        if init_image_tensor is not None:  # :220-225 (dissimlarity_loss.sum() * Config.MS_SSIM_scale)
+            from oracle.ms_ssim import structural_dissimilarity_loss
+
+            loss_sum = loss_sum + structural_dissimilarity_loss(denoised_prediction, init_image_tensor).sum() * config.MS_SSIM_scale
         grad_tensor += torch.autograd.grad(loss_sum, denoised_prediction)[0]  # :226
         conditon_function.last_grad_tensor = grad_tensor.detach().clone()
         if not torch.isnan(grad_tensor).any():  # :228

@@ -238,22 +238,30 @@ def test_config_c1_full_size_against_oracle():
     assert rel <= GRAD_REL_MAX, rel
 
 
-def test_init_image_branch_adds_the_ms_ssim_gradient():
-    """sample.py:220-225: with an init image the (stock-torch) MS-SSIM term is added to the guidance gradient before the VJP."""
-    from clip_diffusion_b200.sample import GuidanceStep
-
-    s = _setup(size=192)
-    init = torch.tanh(torch.randn(1, 3, 192, 192, generator=torch.Generator().manual_seed(5))).cuda()
+def test_init_image_branch_matches_the_oracle():
+    """sample.py:220-225: with an init image the MS-SSIM dissimilarity term (csrc/msssim.cu) is added to the guidance gradient before
+    the UNet VJP; whole cond_fn against the oracle with the same term (oracle/ms_ssim.py)."""
     import copy
 
+    from clip_diffusion_b200.sample import GuidanceStep
+    from oracle.cond_fn import make_conditon_function
+
+    s = _setup(size=192)
+    init = torch.tanh(torch.randn(1, 3, 192, 192, generator=torch.Generator().manual_seed(5)))
     cfg = copy.copy(s["cfg"])
-    cfg.MS_SSIM_scale, cfg.LPIPS_scale = 2000.0, 0.0
-    t = s["diffusion"].model_timesteps(torch.tensor([30], device="cuda"))
+    cfg.MS_SSIM_scale, cfg.LPIPS_scale = 20000.0, 0.0
+    ct = 30
+    f = make_conditon_function(s["diffusion"], s["unet_cpu"], s["ref"], s["text"], lambda: ct, cfg, s["record_source"], init_image_tensor=init)
+    expected = f(s["x"], s["diffusion"].model_timesteps(torch.tensor([ct])))
+    t = s["diffusion"].model_timesteps(torch.tensor([ct], device="cuda"))
     outs = []
-    for img in (None, init):
+    for img in (None, init.cuda()):
         step = GuidanceStep(s["diffusion"], s["unet_gpu"], s["mine"], s["text_gpu"], config=cfg, record_source=s["record_source"], init_image_tensor=img)
-        step.current_timestep = 30
-        step.cond_fn(s["x"].cuda(), t)
+        step.current_timestep = ct
+        got = step.cond_fn(s["x"].cuda(), t)
         outs.append(step.last_grad_tensor.clone())
-    diff = (outs[1] - outs[0])
-    assert torch.isfinite(diff).all() and diff.abs().max().item() > 0
+    diff = outs[1] - outs[0]
+    assert torch.isfinite(diff).all() and diff.abs().max().item() > 0  # the term really contributed
+    rel_gt = ((outs[1].cpu().view_as(f.last_grad_tensor) - f.last_grad_tensor).norm() / f.last_grad_tensor.norm()).item()
+    rel = ((got.cpu() - expected).norm() / expected.norm()).item()
+    assert rel_gt <= GRAD_REL_MAX and rel <= GRAD_REL_MAX, (rel_gt, rel)

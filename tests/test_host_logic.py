@@ -181,24 +181,29 @@ def test_group_norm32_stock_path_spells_the_resblock_arithmetic():
     assert torch.allclose(gn(x, scale_shift=ss, silu=True), want, atol=1e-6)
 
 
-def test_ms_ssim_restatement_properties():
-    """losses.ms_ssim (restated pytorch_msssim.MS_SSIM, parity unpinned): identity, symmetry, monotone in noise, differentiable."""
-    from clip_diffusion_b200.losses import ms_ssim, structural_dissimilarity_loss
+def test_ms_ssim_oracle_properties():
+    """oracle.ms_ssim (restated pytorch_msssim.MS_SSIM, parity unpinned): identity, symmetry, monotone in noise, differentiable; the
+    product's structural_dissimilarity_loss is CUDA-only and refuses CPU tensors."""
+    from clip_diffusion_b200 import _lib
+    from clip_diffusion_b200.losses import structural_dissimilarity_loss
+    from oracle.ms_ssim import ms_ssim
+    from oracle.ms_ssim import structural_dissimilarity_loss as oracle_loss
 
     g = torch.Generator().manual_seed(0)
-    x = torch.rand(2, 3, 176, 192, generator=g)
-    assert abs(ms_ssim(x, x).item() - 1.0) < 1e-6
-    vals = [ms_ssim(x, (x + s * torch.randn(x.shape, generator=g)).clamp(0, 1)).item() for s in (0.02, 0.1, 0.3)]
-    assert 1.0 > vals[0] > vals[1] > vals[2] > 0.0
-    y = torch.rand(2, 3, 176, 192, generator=g)
-    assert abs(ms_ssim(x, y).item() - ms_ssim(y, x).item()) < 1e-6
+    x = torch.rand(1, 3, 192, 192, generator=g, dtype=torch.float64)
+    y = torch.rand(1, 3, 192, 192, generator=g, dtype=torch.float64)
+    assert abs(ms_ssim(x, x).item() - 1.0) < 1e-9
+    vals = [ms_ssim(x, (x + s * torch.randn(x.shape, generator=g, dtype=torch.float64)).clamp(0, 1)).item() for s in (0.02, 0.1, 0.3)]
+    assert vals[0] > vals[1] > vals[2] > 0
+    assert abs(ms_ssim(x, y).item() - ms_ssim(y, x).item()) < 1e-9
     xx = (x * 2 - 1).requires_grad_()
-    loss = structural_dissimilarity_loss(xx, y * 2 - 1)
-    (gr,) = torch.autograd.grad(loss, xx)
-    assert 0.0 < loss.item() < 1.0 and torch.isfinite(gr).all() and gr.abs().max().item() > 0
+    loss = oracle_loss(xx, y * 2 - 1)
+    (gx,) = torch.autograd.grad(loss, xx)
+    assert 0 < loss.item() < 1 and torch.isfinite(gx).all() and gx.abs().max().item() > 0
     with pytest.raises(ValueError):
         ms_ssim(x[..., :100, :100], y[..., :100, :100])
-
+    with pytest.raises(_lib.ClipGuideError):
+        structural_dissimilarity_loss(x.float(), y.float())
 
 def test_guided_diffusion_checkpoint_key_mapping_covers_the_whole_unet():
     """the reference loads a guided-diffusion checkpoint with model.load_state_dict (models.py:118-124); the key

@@ -177,3 +177,27 @@ def test_loss_values_and_clamp_factor_are_bit_reproducible():
     for v in vals[1:]:
         assert v[:4] == vals[0][:4] and torch.equal(v[4], vals[0][4])
     assert abs(vals[0][2] - float((x.double() ** 2).sum())) / vals[0][2] < 1e-5
+
+
+@pytest.mark.parametrize("H,W", [(192, 192), (256, 320), (512, 512)])
+def test_ms_ssim_dissimilarity_kernel_matches_the_float64_oracle(H, W):
+    """N3 (sample.py:220-225, losses.py:48-54): 1 - MS-SSIM value and analytic gradient from csrc/msssim.cu against autograd of the
+    float64 restatement of pytorch_msssim (oracle/ms_ssim.py; the package itself is un-vendored: parity unpinned)."""
+    from clip_diffusion_b200 import losses as L
+    from oracle.ms_ssim import structural_dissimilarity_loss as oracle_loss
+
+    g = torch.Generator().manual_seed(H + W)
+    base = torch.tanh(torch.randn(1, 3, H, W, generator=g))
+    image = base.clone()
+    x = (base + 0.15 * torch.randn(1, 3, H, W, generator=g)).clamp(-1, 1)
+    xr = x.double().requires_grad_()
+    ref = oracle_loss(xr, image.double())
+    (gref,) = torch.autograd.grad(ref, xr)
+    xc = x.cuda().requires_grad_()
+    out = L.structural_dissimilarity_loss(xc, image.cuda())
+    (gout,) = torch.autograd.grad(out * 3.0, xc)
+    assert abs(out.item() - ref.item()) < 2e-5 * max(1.0, abs(ref.item())), (out.item(), ref.item())
+    assert _rel(gout.cpu().double() / 3.0, gref) < 2e-4
+    # identical images: dissimilarity 0
+    same = L.structural_dissimilarity_loss(image.cuda(), image.cuda())
+    assert abs(same.item()) < 1e-5
