@@ -36,8 +36,8 @@ WORKLOADS = {
     "c2": (512, ("ViT-B/16",), 16, 16, 1, 250, "512x512 uncond guided-diffusion UNet + ViT-B/16, 16 overview + 16 inner cutouts, DDIM-250"),
     "c3": (512, ("ViT-B/32", "ViT-B/16", "ViT-L/14"), 32, 32, 1, 250, "512x512 UNet + ViT-B/32+B/16+L/14 ensemble, 64 cutouts per model, tv+range"),
     "target": (512, ("ViT-L/14",), 32, 32, 1, 250, "512x512 UNet + ViT-L/14, 64 cutouts (north_star target)"),
-    "c4": (512, ("ViT-B/32", "ViT-B/16", "ViT-L/14"), 8, 8, 1, 250, "512x512 UNet + B/32+B/16+L/14 with aesthetic-predictor loss (aesthetic_scale 500), 16 cutouts per model; "
-           "the init-image LPIPS/MS-SSIM terms of config 4 are outside this path (SURVEY 8(f) N3)"),
+    "c4": (512, ("ViT-B/32", "ViT-B/16", "ViT-L/14"), 8, 8, 1, 250, "512x512 UNet + B/32+B/16+L/14 with aesthetic-predictor loss (aesthetic_scale 500) and a synthetic init image "
+           "(MS-SSIM dissimilarity term, MS_SSIM_scale 1000; the LPIPS VGG network is un-vendored and left out), 16 cutouts per model"),
     "c5": (768, ("ViT-L/14@336px",), 64, 64, 1, 250, "768x768 UNet + ViT-L/14@336px, 128 cutouts (cutout-scaling sweep, smallest point)"),
     "c5-512": (768, ("ViT-L/14@336px",), 256, 256, 1, 250, "768x768 UNet + ViT-L/14@336px, 512 cutouts (cutout-scaling sweep, largest point; shard over 8 GPUs)"),
     "clip-only": (512, ("ViT-L/14",), 32, 32, 1, 250, "ViT-L/14, 64 cutouts, guidance gradient only (no UNet)"),
@@ -369,10 +369,13 @@ def main():
         buffers and (profile=True) K more steps with CUDA events around every C-ABI call for the kernel rooflines."""
         n_over, n_inner = scaled_cuts(args.workload, world, scaling)
         cfg = make_cfg(n_over, n_inner, batches)
+        init_image = None
         if args.workload == "c4":
             cfg.aesthetic_scale = 500
+            cfg.MS_SSIM_scale, cfg.LPIPS_scale = 1000.0, 0.0
+            init_image = torch.tanh(torch.randn(1, 3, size, size, generator=torch.Generator().manual_seed(9))).to(dev)
         guidance = GuidanceStep(diffusion, unet, clip_models, text, aesthetic_predictors=predictors, config=cfg, rank=rank, world_size=world,
-                                range_scale=150.0 if args.workload == "c3" else 0.0)
+                                range_scale=150.0 if args.workload == "c3" else 0.0, init_image_tensor=init_image)
 
         def step(x, i):
             if clip_only:

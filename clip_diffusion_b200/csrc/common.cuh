@@ -62,6 +62,13 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 static inline cudaStream_t cg_stream(void* s) { return (cudaStream_t)s; }
+// current device ordinal, clamped to the size of the per-device caches (function attributes and SM counts are per device)
+constexpr int CG_MAX_DEVICES = 64;
+static inline int cg_device_index() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : (dev >= CG_MAX_DEVICES ? CG_MAX_DEVICES - 1 : dev);
+}
 
 // Deterministic cross-block reductions (loss values, sum of squares of the guidance gradient): every block stores its partial in a
 // library-owned scratch buffer and the LAST block to arrive (atomic ticket -- the only atomic, and order independent) adds the

@@ -959,10 +959,11 @@ extern "C" int cg_cutouts_fwd(const float* x_in, int H, int W, const cg_cut_t* c
   CG_LAUNCH_CHECK();
   {
     const size_t tmp_bytes = sizeof(float) * RT * (size_t)tmp_ld;
-    static size_t configured = 40 * 1024;  // static shared memory (weights, first taps) shares the 48 KB default limit
-    if (tmp_bytes > configured) {
+    static size_t configured[CG_MAX_DEVICES] = {};  // per device; static shared memory (weights, first taps) shares the 48 KB default limit
+    const int dev = cg_device_index();
+    if (tmp_bytes > 40 * 1024 && tmp_bytes > configured[dev]) {
       CG_CUDA(cudaFuncSetAttribute(resample_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmp_bytes));
-      configured = tmp_bytes;
+      configured[dev] = tmp_bytes;
     }
     resample_fwd_kernel<<<dim3((cs + RT - 1) / RT, U), 256, tmp_bytes, s>>>(x_in, H, W, ucuts, U, taps, left, wfw, cs, aug_h->input01, tmp_ld, base);
     CG_LAUNCH_CHECK();

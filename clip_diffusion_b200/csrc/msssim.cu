@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(TX * TY) ms_maps_kernel(const float* pyr, floa
   const int ox0 = blockIdx.x * TX, oy0 = blockIdx.y * TY;
   const float* X = pyr + L.img_off + (size_t)c * L.H * L.W;
   const float* Y = X + P.pyr_half;
-  const int tid = threadIdx.y * TX + threadIdx.x;
+  const int tid = threadIdx.x, tx = tid & (TX - 1), ty = tid / TX;  // 1-D block of TX*TY threads (block_sum assumes one)
   for (int i = tid; i < (TY + HALO) * (TX + HALO); i += TX * TY) {
     const int r = i / (TX + HALO), q = i - r * (TX + HALO);
     const int gy = oy0 + r, gx = ox0 + q;
@@ -93,18 +93,18 @@ __global__ void __launch_bounds__(TX * TY) ms_maps_kernel(const float* pyr, floa
     h[0][r][q] = a; h[1][r][q] = b; h[2][r][q] = aa; h[3][r][q] = bb; h[4][r][q] = ab;
   }
   __syncthreads();
-  const int oy = oy0 + threadIdx.y, ox = ox0 + threadIdx.x;
+  const int oy = oy0 + ty, ox = ox0 + tx;
   float m = 0.f;
   if (oy < L.vh && ox < L.vw) {
     float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
     for (int t = 0; t < WIN; ++t) {
       const float w = c_win[t];
-      mu1 = fmaf(w, h[0][threadIdx.y + t][threadIdx.x], mu1);
-      mu2 = fmaf(w, h[1][threadIdx.y + t][threadIdx.x], mu2);
-      e11 = fmaf(w, h[2][threadIdx.y + t][threadIdx.x], e11);
-      e22 = fmaf(w, h[3][threadIdx.y + t][threadIdx.x], e22);
-      e12 = fmaf(w, h[4][threadIdx.y + t][threadIdx.x], e12);
+      mu1 = fmaf(w, h[0][ty + t][tx], mu1);
+      mu2 = fmaf(w, h[1][ty + t][tx], mu2);
+      e11 = fmaf(w, h[2][ty + t][tx], e11);
+      e22 = fmaf(w, h[3][ty + t][tx], e22);
+      e12 = fmaf(w, h[4][ty + t][tx], e12);
     }
     const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
     const float s11 = e11 - mu1 * mu1, s22 = e22 - mu2 * mu2, s12 = e12 - mu1 * mu2;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(TX * TY) ms_grad_kernel(const float* pyr, cons
   const int c = blockIdx.z;
   const int qx0 = blockIdx.x * TX, qy0 = blockIdx.y * TY;
   const size_t plane = (size_t)L.vh * L.vw;
-  const int tid = threadIdx.y * TX + threadIdx.x;
+  const int tid = threadIdx.x, tx = tid & (TX - 1), ty = tid / TX;
   // map pixels p with py in [qy0 - 10, qy0 + TY), px in [qx0 - 10, qx0 + TX)
   for (int i = tid; i < (TY + HALO) * (TX + HALO); i += TX * TY) {
     const int r = i / (TX + HALO), q = i - r * (TX + HALO);
@@ -189,15 +189,15 @@ __global__ void __launch_bounds__(TX * TY) ms_grad_kernel(const float* pyr, cons
     hv[0][r][q] = a; hv[1][r][q] = b; hv[2][r][q] = d;
   }
   __syncthreads();
-  const int qy = qy0 + threadIdx.y, qx = qx0 + threadIdx.x;
+  const int qy = qy0 + ty, qx = qx0 + tx;
   if (qy < L.H && qx < L.W) {
     float a = 0.f, b = 0.f, d = 0.f;
 #pragma unroll
     for (int t = 0; t < WIN; ++t) {
       const float w = c_win[t];
-      a = fmaf(w, hv[0][threadIdx.y + HALO - t][threadIdx.x], a);
-      b = fmaf(w, hv[1][threadIdx.y + HALO - t][threadIdx.x], b);
-      d = fmaf(w, hv[2][threadIdx.y + HALO - t][threadIdx.x], d);
+      a = fmaf(w, hv[0][ty + HALO - t][tx], a);
+      b = fmaf(w, hv[1][ty + HALO - t][tx], b);
+      d = fmaf(w, hv[2][ty + HALO - t][tx], d);
     }
     const size_t o = (size_t)c * L.H * L.W + (size_t)qy * L.W + qx;
     const float xv = pyr[L.img_off + o], yv = pyr[P.pyr_half + L.img_off + o];
@@ -288,7 +288,7 @@ extern "C" int cg_ms_ssim_dissimilarity_fwd_bwd(const float* x, const float* y, 
   }
   for (int l = 0; l < LEVELS; ++l) {
     const Level& L = P.lv[l];
-    ms_maps_kernel<<<dim3((L.vw + TX - 1) / TX, (L.vh + TY - 1) / TY, C), dim3(TX, TY), 0, s>>>(pyr, pyr, partials, P, l);
+    ms_maps_kernel<<<dim3((L.vw + TX - 1) / TX, (L.vh + TY - 1) / TY, C), dim3(TX * TY), 0, s>>>(pyr, pyr, partials, P, l);
     CG_LAUNCH_CHECK();
   }
   ms_scalars_kernel<<<1, 256, 0, s>>>(partials, P, grad_scale, loss, kcoef);
@@ -296,7 +296,7 @@ extern "C" int cg_ms_ssim_dissimilarity_fwd_bwd(const float* x, const float* y, 
   if (grad) {
     for (int l = 0; l < LEVELS; ++l) {
       const Level& L = P.lv[l];
-      ms_grad_kernel<<<dim3((L.W + TX - 1) / TX, (L.H + TY - 1) / TY, C), dim3(TX, TY), 0, s>>>(pyr, pyr, kcoef, pyr, P, l);
+      ms_grad_kernel<<<dim3((L.W + TX - 1) / TX, (L.H + TY - 1) / TY, C), dim3(TX * TY), 0, s>>>(pyr, pyr, kcoef, pyr, P, l);
       CG_LAUNCH_CHECK();
     }
     ms_up_kernel<<<blocks((size_t)C * H * W), 256, 0, s>>>(pyr, P, accumulate, grad);

@@ -1141,10 +1141,11 @@ int launch_attn_tc(const void* qkv, const void* dctx, int Nimg, int T, int heads
   }
   const size_t opb = (size_t)((p.nblk - 1) * 64 + p.tail_rows) * 128;
   const size_t smem = 1024 + (FWD ? 3 : 4) * opb + (size_t)Depth<FWD>::NPB * (FWD ? TILE_BYTES : 2 * TILE_BYTES) + (FWD ? 1408 : 640 + 256) * 4 + BARS_BYTES;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[CG_MAX_DEVICES] = {};  // function attributes are per device
+  const int dev = cg_device_index();
+  if (smem > configured[dev]) {
     CG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured[dev] = smem;
   }
   CG_CUDA(cg_launch_pdl(attn_tc_kernel<FWD>, dim3(heads, Nimg), dim3(AT_THREADS), smem, s, tq, tqt, td, tdt, p));
   return 0;
@@ -1171,10 +1172,11 @@ int cg_attention_fwd_tc(const void* qkv, int Nimg, int T, int heads, void* ctx, 
   if (rc) return rc;
   const size_t opb = (size_t)((p.nblk - 1) * 64 + p.tail_rows) * 128;
   const size_t smem = 1024 + 3 * opb + 4 * (size_t)TILE_BYTES + (1536 + 128) * 4 + FBARS_BYTES;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[CG_MAX_DEVICES] = {};
+  const int dev = cg_device_index();
+  if (smem > configured[dev]) {
     CG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured[dev] = smem;
   }
   CG_CUDA(cg_launch_pdl(attn_fwd_tc_kernel, dim3(heads, Nimg), dim3(AT_THREADS), smem, s, tq, tqt, p));
   return 0;

@@ -540,23 +540,24 @@ int make_tensor_map(CUtensorMap* out, const void* ptr, long long rows, long long
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int per_device[CG_MAX_DEVICES] = {};
+  const int dev = cg_device_index();
+  if (per_device[dev] == 0) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = CG_NUM_SMS;
+    per_device[dev] = n > 0 ? n : CG_NUM_SMS;
   }
-  return n;
+  return per_device[dev];
 }
 
 template <int BN, int EPI>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t s) {
   constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[CG_MAX_DEVICES] = {};  // function attributes are per device
+  const int dev = cg_device_index();
+  if (!configured[dev]) {
     CG_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured[dev] = true;
   }
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -582,10 +583,11 @@ int dispatch(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
 template <int EPI>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t s) {
   constexpr size_t smem = (size_t)STAGES2 * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[CG_MAX_DEVICES] = {};
+  const int dev = cg_device_index();
+  if (!configured[dev]) {
     CG_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured[dev] = true;
   }
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN2);
   int clusters = num_sms() / 2;
