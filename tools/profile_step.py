@@ -20,7 +20,9 @@ OURS = ("gemm_bf16_tn_kernel", "attn_fwd_kernel", "attn_bwd_", "attn_delta_kerne
         "resample_fwd_kernel", "resample_bwd_kernel", "augment_fwd_kernel", "jitter_fwd_kernel", "jitter_bwd_kernel", "affine_bwd_kernel",
         "tv_kernel", "range_kernel", "sph_", "set_cls_kernel", "proj_fwd_kernel", "proj_bwd_kernel", "tokens_to_bf16_kernel", "patchify_kernel",
         "sumsq_nan_kernel", "finalize_kernel", "nanflag_kernel", "gn_stats_partial_kernel", "gn_finalize_", "gn_apply_", "gn_bwd_partial_kernel",
-        "bias_residual_add_kernel", "resample2x_kernel", "concat2_kernel", "gemm_bf16_tn_pair_kernel", "hist_kernel", "count_kernel", "::apply_kernel")
+        "bias_residual_add_kernel", "resample2x_kernel", "concat2_kernel", "gemm_bf16_tn_pair_kernel", "hist_kernel", "count_kernel", "::apply_kernel",
+        "attn_tc_kernel", "attn_fwd_tc_kernel", "image_losses_kernel", "ms_pool_kernel", "ms_maps_kernel", "ms_scalars_kernel", "ms_grad_kernel", "ms_up_kernel",
+        "producer_stats_kernel", "jitter_bwd_sum_kernel", "randn_like_torch_kernel", "sph_loss_sum_kernel")
 rows = {}
 for ev in prof.events():
     if ev.device_type.name != "CUDA":
