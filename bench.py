@@ -101,10 +101,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def summary(self, t0, t1):
+    def summary(self, t0, t1, t_end=None):
         if self.proc is not None:
             self.proc.terminate()
-        rows = [r for ts, r in self.rows if t0 <= ts <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        rows = ([r for ts, r in self.rows if t0 <= ts <= t1 and len(r) >= 7] or [r for ts, r in self.rows if t0 <= ts <= (t_end or t1) and len(r) >= 7]
+                or [r for _, r in self.rows[-3:] if len(r) >= 7])
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm = sorted(float(r[0]) for r in rows)
@@ -388,13 +389,14 @@ def main():
 
         i = ddim - 1
         x = x_dev
+        # nvidia-smi needs ~0.5 s before its first sample: start it before the warm-up so that it is streaming during the timed regions
+        clocks = ClockSampler(local_rank) if (rank == 0 and profile) else None
         for _ in range(W):
             x = step(x, i)["sample"]
             i = next_i(i)
         res = {"cuts_per_step": (n_over + n_inner) * batches * len(names), "n_over": n_over, "n_inner": n_inner}
         # ---- timed region 1: inputs resident in HBM -------------------------------------------------
         barrier()
-        clocks = ClockSampler(local_rank) if (rank == 0 and profile) else None
         k0 = _lib.kernel_launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         use_range = profile and os.environ.get("CG_BENCH_PROFILER_RANGE") == "1"  # ncu --profile-from-start off: profile the timed region only
@@ -414,7 +416,6 @@ def main():
         res["launches"] = _lib.kernel_launches - k0
         if unet_graphed:  # our GroupNorm / resample / concat kernels replayed inside the UNet's CUDA graphs (one forward + one backward per step)
             res["launches"] += K * unet.own_kernels_per_replay
-        res["clocks"] = clocks.summary(wall0, wall1) if clocks else None
         if not profile:
             return res
         # ---- timed region 2: end to end through host buffers ------------------------------------------
@@ -441,6 +442,8 @@ def main():
         barrier()
         res["prof"], _lib.PROFILE = _lib.PROFILE, None
         res["ms_prof"] = e0.elapsed_time(e1)
+        # samples inside timed region 1; if the region was shorter than the sampling period, the samples of the three timed regions (all under load)
+        res["clocks"] = clocks.summary(wall0, wall1, time.time()) if clocks else None
         return res
 
     main_res = measure(args.scaling, profile=True)

@@ -106,6 +106,15 @@ __device__ __forceinline__ float cg_sum_partials(const float* partials, unsigned
   return block_sum(s, red);
 }
 
+// the same by ONE warp (lane-strided, then a fixed shuffle tree): lets the warps of the last block finish different images in parallel
+__device__ __forceinline__ float cg_sum_partials_warp(const float* partials, unsigned first, unsigned count) {
+  float s = 0.f;
+  for (unsigned i = threadIdx.x & 31; i < count; i += 32) s += __ldcg(partials + first + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
 // Programmatic dependent launch.  The guidance step is a long chain of short dependent kernels (per ViT layer: 9 GEMMs, 3 attention
 // kernels, 4 LayerNorms; many run 10-40 us), so launch latency and kernel prologues (barrier init, TMEM allocation, descriptor
 // prefetch) are a visible share of the step.  Kernels launched through cg_launch_pdl() carry

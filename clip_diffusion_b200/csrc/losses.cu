@@ -9,9 +9,14 @@ namespace {
 __device__ __forceinline__ void per_image_loss(float block_total, float inv, float* loss, const CgScratch& ws, int counter, unsigned block_linear,
                                                unsigned nblocks, unsigned blocks_per_image, unsigned images, float* red) {
   if (cg_last_block(block_total, ws.partials, ws.counters + counter, block_linear, nblocks)) {
-    for (unsigned b = 0; b < images; ++b) {
-      const float t = cg_sum_partials(ws.partials, b * blocks_per_image, blocks_per_image, red);
-      if (threadIdx.x == 0) loss[b] = t * inv;
+    if (images == 1) {
+      const float t = cg_sum_partials(ws.partials, 0, blocks_per_image, red);
+      if (threadIdx.x == 0) loss[0] = t * inv;
+    } else {  // one warp per image (fixed lane-strided order: still deterministic), the warps of the block work in parallel
+      for (unsigned b = threadIdx.x >> 5; b < images; b += blockDim.x >> 5) {
+        const float t = cg_sum_partials_warp(ws.partials, b * blocks_per_image, blocks_per_image);
+        if ((threadIdx.x & 31) == 0) loss[b] = t * inv;
+      }
     }
   }
 }
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(256) range_kernel(const float* __restrict__ x,
 // for NaN.)  W % 128 == 0: a block owns a 32-row x 128-column tile of one plane, like tv_tiled_kernel.  grad (+)= d(tv_scale * TV +
 // range_scale * range)/dx; flag[0] = 1 if any element of the finished grad is NaN (the caller zeroes flag[0..1] is NOT needed: the last
 // block writes it).  loss2 (optional) receives [B][2] = (TV, range) values, deterministic.
+template <int TR>  // rows per tile: 32 for big batches, 8 (one row per warp, no loop: all loads of the CTA in flight at once) when the grid would not fill the GPU
 __global__ void __launch_bounds__(256) image_losses_kernel(const float* __restrict__ x, int C, int H, int W, float tv_scale, float range_scale,
                                                            int accumulate, float* __restrict__ loss2, float* __restrict__ grad, float* __restrict__ flag,
                                                            CgScratch ws) {
@@ -202,10 +208,10 @@ __global__ void __launch_bounds__(256) image_losses_kernel(const float* __restri
   const float* xp = x + (int64_t)plane_id * H * W;
   float* gp = grad + (int64_t)plane_id * H * W;
   const int x0 = blockIdx.x * 128 + lane * 4;
-  const int h0 = blockIdx.y * 32;
+  const int h0 = blockIdx.y * TR;
   float acc_tv = 0.f, acc_rg = 0.f, bad = 0.f;
 #pragma unroll 1
-  for (int r = warp; r < 32; r += 8) {
+  for (int r = warp; r < TR; r += 8) {
     const int h = h0 + r;
     if (h >= H) break;
     const float* row = xp + (int64_t)h * W;
@@ -251,10 +257,10 @@ __global__ void __launch_bounds__(256) image_losses_kernel(const float* __restri
     if (threadIdx.x == 0) { flag[0] = anybad > 0.f ? 1.f : 0.f; flag[1] = anybad; }
     if (loss2) {
       const unsigned per = gridDim.x * gridDim.y * C, images = gridDim.z / C;
-      for (unsigned b = 0; b < images; ++b) {
-        const float a = cg_sum_partials(ws.partials, b * per, per, red);
-        const float c = cg_sum_partials(ws.partials, nblocks + b * per, per, red);
-        if (threadIdx.x == 0) { loss2[2 * b] = a * inv; loss2[2 * b + 1] = c * inv; }
+      for (unsigned b = threadIdx.x >> 5; b < images; b += blockDim.x >> 5) {
+        const float a = cg_sum_partials_warp(ws.partials, b * per, per);
+        const float c = cg_sum_partials_warp(ws.partials, nblocks + b * per, per);
+        if ((threadIdx.x & 31) == 0) { loss2[2 * b] = a * inv; loss2[2 * b + 1] = c * inv; }
       }
     }
   }
@@ -386,7 +392,10 @@ extern "C" int cg_range_loss_fwd_bwd(const float* x, int B, int C, int H, int W,
   CgScratch ws;
   int rc = cg_get_scratch(&ws);
   if (rc) return rc;
-  dim3 grid(grid_for(per_img / 4 + 1, 256), B);
+  // batches: keep the whole grid at ~8 CTAs per SM (the last block's ordered sum grows with the block count)
+  int gx = grid_for(per_img / 4 + 1, 256);
+  if (B > 1) gx = max(1, min(gx, (8 * 148 * 2 + B - 1) / B));
+  dim3 grid(gx, B);
   range_kernel<<<grid, 256, 0, s>>>(x, per_img, grad_scale, accumulate, loss, grad, ws);
   CG_LAUNCH_CHECK();
   return 0;
@@ -430,12 +439,17 @@ extern "C" int cg_image_losses_fwd_bwd(const float* x, int B, int C, int H, int 
                                        float* loss2, float* grad, float* nan_flag, void* stream) {
   CG_REQUIRE(x && grad && nan_flag && B > 0 && C > 0 && H > 0 && W > 0, "cg_image_losses_fwd_bwd: bad arguments");
   CG_REQUIRE(W % 128 == 0 && (((uintptr_t)x | (uintptr_t)grad) & 15) == 0, "cg_image_losses_fwd_bwd: W=%d must be a multiple of 128 and the pointers 16-byte aligned (use cg_tv_loss_fwd_bwd / cg_range_loss_fwd_bwd / cg_any_nan otherwise)", W);
-  const long long tiles = (long long)(W / 128) * ((H + 31) / 32) * B * C;
+  long long tiles = (long long)(W / 128) * ((H + 31) / 32) * B * C;
+  const bool small = tiles < 4 * 148;
+  if (small) tiles = (long long)(W / 128) * ((H + 7) / 8) * B * C;
   CG_REQUIRE((long long)B * C <= 65535 && 3 * tiles <= CG_SCRATCH_FLOATS, "cg_image_losses_fwd_bwd: too many tiles (%lld)", tiles);
   CgScratch ws;
   int rc = cg_get_scratch(&ws);
   if (rc) return rc;
-  image_losses_kernel<<<dim3(W / 128, (H + 31) / 32, B * C), 256, 0, cg_stream(stream)>>>(x, C, H, W, tv_scale, range_scale, accumulate, loss2, grad, nan_flag, ws);
+  if (small)
+    image_losses_kernel<8><<<dim3(W / 128, (H + 7) / 8, B * C), 256, 0, cg_stream(stream)>>>(x, C, H, W, tv_scale, range_scale, accumulate, loss2, grad, nan_flag, ws);
+  else
+    image_losses_kernel<32><<<dim3(W / 128, (H + 31) / 32, B * C), 256, 0, cg_stream(stream)>>>(x, C, H, W, tv_scale, range_scale, accumulate, loss2, grad, nan_flag, ws);
   CG_LAUNCH_CHECK();
   return 0;
 }

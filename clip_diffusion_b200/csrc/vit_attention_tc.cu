@@ -32,7 +32,7 @@
 //             P is recomputed from the saved log-sum-exp; two orientations instead of a transposed smem operand, no atomics,
 //             deterministic.  Rows / columns beyond T are masked (tail block only) or never stored.
 //
-// Measured on B200 (profiles/r02_attention_*.txt), T = 257 x 64 images x 16 heads: forward 108 us, backward 232 us per layer (round 1
+// Measured on B200 (profiles/r02_kernel_rooflines.txt, r02_ncu_vit_kernels_digest.txt), T = 257 x 64 images x 16 heads: forward 102 us, backward 214 us per layer (round 1
 // mma.sync kernels: 104 / 349).  A softmax warp spends ~2900 cycles per 64-column block of which the MUFU-bound share is 1024 (two warps
 // per SM sub-partition, 8 cycles per MUFU.EX2 warp instruction, measured with tools/probes/mufu_probe.cu): the tcgen05.ld latency, the
 // serial max chain, the proxy fence and the barrier round trips of the two warps of a sub-partition run in lock step and leave the MUFU

@@ -99,9 +99,11 @@ def test_gemm_rejects_bad_shapes():
         ops.gemm_bf16_tn(a, b, _lib.EPI_F32)
 
 
-def test_gemm_cta_pair_kernel_in_subprocess():
-    """The cta_group::2 (CTA-pair, 256x256 tile) variant is selected with CG_GEMM_PAIR=1 at library load; run the same
-    parity cases in a child process with that environment (and a timeout: a cluster deadlock must not hang the suite)."""
+@pytest.mark.parametrize("force", [{"CG_GEMM_PAIR": "1"}, {"CG_GEMM_PAIR": "0", "CG_GEMM_BN": "128"}, {"CG_GEMM_PAIR": "0", "CG_GEMM_BN": "256"}],
+                         ids=["pair256x256", "bn128", "bn256"])
+def test_gemm_forced_tile_variant_in_subprocess(force):
+    """The tile variant is chosen per problem (choose_tile); CG_GEMM_PAIR / CG_GEMM_BN force one at library load.  Run the same parity
+    cases on EVERY variant in a child process with that environment (and a timeout: a cluster deadlock must not hang the suite)."""
     import os
     import subprocess
     import sys
@@ -129,7 +131,7 @@ torch.cuda.synchronize()
 print("WORST", worst)
 assert worst < 1e-3, worst
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CG_GEMM_PAIR="1")
+    env = dict(os.environ, **force)
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "WORST" in res.stdout

@@ -61,6 +61,11 @@ for (B, H, W) in [(1, 512, 512), (1, 768, 768), (16, 1024, 1024), (64, 1024, 102
     nb = 2 * x.numel() * 4
     row("tv_loss value+grad [%d,3,%d,%d]" % (B, H, W), timeit(lambda: _lib.call("cg_tv_loss_fwd_bwd", P(x), B, 3, H, W, 1.0, 0, P(loss), P(g))), nb)
     row("range_loss value+grad [%d,3,%d,%d]" % (B, H, W), timeit(lambda: _lib.call("cg_range_loss_fwd_bwd", P(x), B, 3, H, W, 1.0, 0, P(loss), P(g))), nb)
+for (B, H, W) in [(1, 512, 512), (1, 768, 768), (64, 1024, 1024)] if want("losses") else []:
+    x = torch.tanh(torch.randn(B, 3, H, W, device="cuda")) * 1.1
+    g = torch.zeros_like(x); loss2 = torch.empty(B, 2, device="cuda"); flag = torch.zeros(2, device="cuda")
+    row("fused TV+range+NaN flag, grad += [%d,3,%d,%d]" % (B, H, W),
+        timeit(lambda: _lib.call("cg_image_losses_fwd_bwd", P(x), B, 3, H, W, 1.0, 1.0, 1, P(loss2), P(g), P(flag))), 3 * x.numel() * 4)
 for (N, E) in [(64, 768), (4096, 768), (65536, 768)] if want("losses") else []:
     e = torch.randn(N, E, device="cuda"); t = torch.randn(1, E, device="cuda"); d = torch.empty_like(e)
     row("spherical loss+grad N=%d E=%d" % (N, E), timeit(lambda: _lib.call("cg_spherical_loss_fwd_bwd", P(e), P(t), None, N, 1, E, 1.0, None, P(d))), (2 * N + 1) * E * 4)
