@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libclipguide_b200.so")
+LIB_PATH = os.environ.get("CLIPGUIDE_B200_LIB") or os.path.join(_HERE, "csrc", "libclipguide_b200.so")  # the override is for developer builds (make trace)
 
 CG_FMT_F32_NCHW = 0
 CG_FMT_BF16_PATCH = 1

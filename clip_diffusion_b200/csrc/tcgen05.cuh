@@ -10,17 +10,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting warp is parked until the phase completes (or the hint expires) instead of re-issuing
+// the test in a tight loop.  Without the hint the spinning issuer / producer warps of the attention kernels took a large share of
+// the issue slots of their SM sub-partitions (ncu: a quarter of all executed instructions were try_wait + branch) and slowed the
+// warps doing arithmetic on the same sub-partition.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
       "@P1 bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
       "}" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {

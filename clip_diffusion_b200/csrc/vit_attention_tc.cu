@@ -115,6 +115,73 @@ __device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const uint3
   for (int j = 0; j < 4; ++j) st256g(dst + 16 * j, w + 8 * j);
 }
 
+// ---- CUDA-core helpers of the "edge token" path (T = 64 m + 1: the last token is handled outside the tensor-core pipeline)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ void unpack8(const uint4 u, float* f) {
+  f[0] = bf_lo(u.x); f[1] = bf_hi(u.x); f[2] = bf_lo(u.y); f[3] = bf_hi(u.y);
+  f[4] = bf_lo(u.z); f[5] = bf_hi(u.z); f[6] = bf_lo(u.w); f[7] = bf_hi(u.w);
+}
+__device__ __forceinline__ float dot8(const uint4 a, const float* f, float acc) {
+  acc = fmaf(bf_lo(a.x), f[0], acc); acc = fmaf(bf_hi(a.x), f[1], acc); acc = fmaf(bf_lo(a.y), f[2], acc); acc = fmaf(bf_hi(a.y), f[3], acc);
+  acc = fmaf(bf_lo(a.z), f[4], acc); acc = fmaf(bf_hi(a.z), f[5], acc); acc = fmaf(bf_lo(a.w), f[6], acc); acc = fmaf(bf_hi(a.w), f[7], acc);
+  return acc;
+}
+// dot product of row `r` of a 128B-swizzled [rows x 64] bf16 operand buffer with a 64-float vector in registers
+__device__ __forceinline__ float dot_row64(uint32_t buf, int r, const float* f) {
+  const uint32_t rowb = buf + (uint32_t)r * 128u, x = (uint32_t)(r & 7);
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    a0 = dot8(lds128(rowb + (((uint32_t)c ^ x) << 4)), f + 8 * c, a0);
+    a1 = dot8(lds128(rowb + (((uint32_t)(c + 1) ^ x) << 4)), f + 8 * c + 8, a1);
+  }
+  return a0 + a1;
+}
+// dot product of two packed groups of 8 bf16
+__device__ __forceinline__ float dot8p(const uint4 a, const uint4 b, float acc) {
+  acc = fmaf(bf_lo(a.x), bf_lo(b.x), acc); acc = fmaf(bf_hi(a.x), bf_hi(b.x), acc); acc = fmaf(bf_lo(a.y), bf_lo(b.y), acc); acc = fmaf(bf_hi(a.y), bf_hi(b.y), acc);
+  acc = fmaf(bf_lo(a.z), bf_lo(b.z), acc); acc = fmaf(bf_hi(a.z), bf_hi(b.z), acc); acc = fmaf(bf_lo(a.w), bf_lo(b.w), acc); acc = fmaf(bf_hi(a.w), bf_hi(b.w), acc);
+  return acc;
+}
+// dot product of row ra of buffer A with row rb of buffer B (both 128B-swizzled [rows x 64] bf16).  Deliberately a ROLLED loop: the edge
+// paths run once per tile and must stay small -- the forward kernel slowed down by 30-60% in every role when its code grew from 54 KB to
+// 99 KB (instruction-cache misses), measured with the time-line probes.
+__device__ __forceinline__ float dot_rows(uint32_t bufa, int ra, uint32_t bufb, int rb) {
+  const uint32_t pa = bufa + (uint32_t)ra * 128u, xa = (uint32_t)(ra & 7) << 4, pb = bufb + (uint32_t)rb * 128u, xb = (uint32_t)(rb & 7) << 4;
+  float acc = 0.f;
+#pragma unroll 1
+  for (uint32_t c = 0; c < 128u; c += 16u) acc = dot8p(lds128(pa + (c ^ xa)), lds128(pb + (c ^ xb)), acc);
+  return acc;
+}
+// the same, unrolled with two accumulators (16 loads in flight)
+__device__ __forceinline__ float dot_rows2(uint32_t bufa, int ra, uint32_t bufb, int rb) {
+  const uint32_t pa = bufa + (uint32_t)ra * 128u, xa = (uint32_t)(ra & 7) << 4, pb = bufb + (uint32_t)rb * 128u, xb = (uint32_t)(rb & 7) << 4;
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (uint32_t c = 0; c < 128u; c += 32u) {
+    a0 = dot8p(lds128(pa + (c ^ xa)), lds128(pb + (c ^ xb)), a0);
+    a1 = dot8p(lds128(pa + ((c + 16u) ^ xa)), lds128(pb + ((c + 16u) ^ xb)), a1);
+  }
+  return a0 + a1;
+}
+// row `r` (any row: the swizzle is undone) of such a buffer -> 64 floats
+__device__ __forceinline__ void load_row64(uint32_t buf, int r, float* f) {
+  const uint32_t rowb = buf + (uint32_t)r * 128u, x = (uint32_t)(r & 7);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) unpack8(lds128(rowb + (((uint32_t)c ^ x) << 4)), f + 8 * c);
+}
+
 // Pipeline depths.  S (and dP) blocks: 4 x 64 TMEM columns in the forward, 3 x 128 in the backward (the accumulators need the
 // rest of the 512 columns); staging buffers: 4 x 16 KB in the forward, 2 x 32 KB (P^T and dS^T) in the backward.
 template <bool FWD> struct Depth { static constexpr int NSB = FWD ? 4 : 3, NPB = FWD ? 4 : 2; };
@@ -168,7 +235,10 @@ struct BlkIt {
 };
 
 struct AttnParams {
-  int T, heads, ntiles, nblk, tail_rows;  // tail_rows: rows of the last 64-row block, rounded up to 16
+  int T, heads, ntiles, nblk, tail_rows;  // tiles / 64-wide blocks of the tensor-core pipeline; tail_rows: rows of its last block, rounded up to 16
+  int nitems;                             // forward (persistent kernel): (image, head) items = Nimg * heads
+  int edge, nblk_ld, ld_tail;             // edge = 1: T = 64 m + 1, token T-1 is handled on CUDA cores and the pipeline covers T-1 tokens;
+                                          // operand blocks LOADED per operand (pipeline blocks + the edge block) and rows of the last one
   float scale;
   __nv_bfloat16* ctx;        // forward out [Nimg*T, D]
   float* lse;                // [Nimg, heads, T]  (forward out, backward in)
@@ -180,7 +250,7 @@ struct AttnParams {
 #ifdef CG_ATTN_TRACE
 #define TR(slot, idx, ev)                                                                                   \
   do {                                                                                                      \
-    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0)                \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == (gridDim.y >> 1) && (threadIdx.x & 31) == 0) /* a CTA of a later wave: warm instruction cache */                \
       p.trace[(((slot) * 64 + (idx)) << 3) + (ev)] = clock64();                                             \
   } while (0)
 #else
@@ -709,26 +779,45 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   }
 }
 
-// ------------------------------------------------------------------------------------------------ forward (online softmax)
-// One pass over the score blocks.  Block g = tile * nblk + blk goes to warpgroup g & 1; each warpgroup keeps ITS OWN running
-// reference maximum and row sum and accumulates its blocks into ITS OWN O accumulator in TMEM, so the two never wait for each
-// other; the epilogue merges the two partial results (flash-decoding style).  The reference maximum only moves when a block
-// exceeds it by more than 2^8 (P stays <= 256: exact in fp32 / bf16 range), in which case the warpgroup rescales its accumulator
-// in TMEM (tcgen05.ld / tcgen05.st) -- rare after the first block.
+// ------------------------------------------------------------------------------------------------ forward (online softmax, persistent)
+// PERSISTENT kernel: one CTA per SM walks the (image, head) items w = blockIdx.x, blockIdx.x + gridDim.x, ... and the block stream runs
+// ACROSS items: the S MMAs, the softmax and the P V MMAs of item i+1 start while the last tile of item i is still being finished and
+// written out, Q / K of item i+1 are loaded as soon as the last S MMA of item i has completed, V is double buffered.  (One CTA per item
+// spent ~35% of its life outside the steady state: CTA launch + barrier / TMEM set-up ~3700 cycles, first TMA round trip ~1000, epilogue
+// tail ~3000 of ~26000 -- measured with the time-line probes.)
+//
+// One pass over the score blocks of an item.  Block gg (running index over all items) goes to warpgroup gg & 1; each warpgroup keeps
+// ITS OWN running reference maximum and row sum and accumulates its blocks into ITS OWN O accumulator in TMEM, so the two never wait for
+// each other; the epilogue merges the partial results (flash-decoding style).  The reference maximum only moves when a block exceeds it
+// by more than 2^8 (P stays <= 256: exact in fp32 / bf16 range), in which case the warpgroup rescales its accumulator in TMEM
+// (tcgen05.ld / tcgen05.st) -- rare after the first block.
+//
+// T = 64 m + 1 (ViT-L/14: 257): the LAST token ("edge") stays out of the tensor-core pipeline, which then sees only full blocks and
+// tiles (a 1-row tile costs the pipeline nblk dependent S -> softmax -> PV round trips: 25% of the item).  The epilogue warps compute
+// the edge query row against all keys on CUDA cores while the first tile is in flight, and fold the edge key into every other row as
+// a third partial result (one column: s_e = q . k_e, accumulator v_e, row sum 1) when they merge a tile.
+//
+//   warps 0 / 1   S = Q K^T of the even / odd blocks        warp 2   O += P V, TMEM allocation        warp 3   TMA producer
+//   warps 4-11    two softmax warpgroups                    warps 12-15   epilogue + edge token
 //   TMEM: S buffers 4 x 64 columns [0, 256); O[wg][tile & 1] at 256 + (2 wg + (tile & 1)) * 64.
 struct FBars {
   uint32_t base;
-  __device__ __forceinline__ uint32_t sfull(int b) const { return base + 8u * b; }
-  __device__ __forceinline__ uint32_t sfree(int b) const { return base + 32u + 8u * b; }
-  __device__ __forceinline__ uint32_t pready(int b) const { return base + 64u + 8u * b; }
-  __device__ __forceinline__ uint32_t pfree(int b) const { return base + 96u + 8u * b; }
-  __device__ __forceinline__ uint32_t accfull(int a) const { return base + 128u + 8u * a; }  // a = 2 wg + (tile & 1)
-  __device__ __forceinline__ uint32_t accfree(int a) const { return base + 160u + 8u * a; }
-  __device__ __forceinline__ uint32_t lready(int t) const { return base + 192u + 8u * t; }
-  __device__ __forceinline__ uint32_t op(int o, int blk) const { return base + 216u + 8u * (o * MAX_BLK + blk); }
-  __device__ __forceinline__ uint32_t tmem_slot() const { return base + 216u + 8u * (3 * MAX_BLK); }
+  __device__ __forceinline__ uint32_t sfull(int b) const { return base + 8u * b; }                       // S block in TMEM buffer b            (tcgen05.commit)
+  __device__ __forceinline__ uint32_t sfree(int b) const { return base + 32u + 8u * b; }                 // its warpgroup has read it           (4 warps)
+  __device__ __forceinline__ uint32_t pready(int b) const { return base + 64u + 8u * b; }                // staging buffer b is written         (4 warps)
+  __device__ __forceinline__ uint32_t pfree(int b) const { return base + 96u + 8u * b; }                 // the P V MMAs have consumed it       (tcgen05.commit)
+  __device__ __forceinline__ uint32_t accfull(int a) const { return base + 128u + 8u * a; }              // accumulator a = 2 wg + (tile & 1)   (tcgen05.commit)
+  __device__ __forceinline__ uint32_t accfree(int a) const { return base + 160u + 8u * a; }              // epilogue has read it                (4 warps)
+  __device__ __forceinline__ uint32_t mready(int a, uint32_t r) const { return base + 192u + 8u * (2u * a + r); }  // row maxima / sums of use r (mod 2) of slot a (4 warps)
+  __device__ __forceinline__ uint32_t opq(int blk) const { return base + 256u + 8u * blk; }              // operand blocks                      (TMA)
+  __device__ __forceinline__ uint32_t opk(int blk) const { return base + 296u + 8u * blk; }
+  __device__ __forceinline__ uint32_t opv(int vb, int blk) const { return base + 336u + 8u * (vb * MAX_BLK + blk); }
+  __device__ __forceinline__ uint32_t qkfree() const { return base + 416u; }                             // Q / K of the item are no longer read (2 issuers + 4 epilogue warps)
+  __device__ __forceinline__ uint32_t vfree(int vb) const { return base + 424u + 8u * vb; }              // V buffer vb                          (1 issuer + 4 epilogue warps)
+  __device__ __forceinline__ uint32_t tmem_slot() const { return base + 440u; }
 };
-constexpr uint32_t FBARS_BYTES = 216 + 8 * 3 * MAX_BLK + 16;
+constexpr uint32_t FBARS_BYTES = 448 + 16;
+constexpr uint32_t FWD_FLOATS = 4096 + 640;  // sm[4][4][128], sl[4][4][128], edge scratch [640]
 constexpr float RESCALE_LOG2 = 8.f;
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
@@ -743,26 +832,119 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// The edge token of the forward (T = Tp + 1, Tp a multiple of 64), on CUDA cores, by the 128 threads of the four epilogue warps; a
+// Both operand rows of a dot product are read from shared memory chunk by chunk (the fixed row as broadcast loads) instead of keeping
+// the fixed row in registers: a spilled register costs an L2 round trip in these kernels (shared memory leaves ~28 KB of L1), and
+// the compiler hoists the unpacking of a register-resident row out of the key loop (64 live floats -> spills).
+//   * the edge QUERY row against all T keys -> ctx_row (64 bf16), lse_out
+//   * the edge KEY against this thread's rows rl and 128 + rl -> returned (log2 units, -inf beyond Tp): the third partial result of the
+//     tile merge;  v_e as floats -> pvec[552 .. 616)
+// scratch pvec: [288] scores / numerators, [8] reductions, [4][32] float2 partial outputs, [64] v_e
+__device__ __forceinline__ float2 fwd_edge_token(uint32_t sQ, uint32_t sK, uint32_t sV, int Tp, float sl2, float* pvec, __nv_bfloat16* ctx_row, float* lse_out) {
+  const int rl = threadIdx.x & 127, q = rl >> 5, lane = rl & 31;
+  const int T = Tp + 1;
+  float* red = pvec + 288;
+  float2* part = reinterpret_cast<float2*>(pvec + 296);
+  float* vedge = pvec + 552;
+  float mx;
+  {
+    // corner s_ee: every warp computes it redundantly (rows Tp of Q and K are not permuted by the swizzle: Tp % 8 == 0)
+    const uint32_t wq = lds32(sQ + (uint32_t)Tp * 128u + (uint32_t)lane * 4u), wk = lds32(sK + (uint32_t)Tp * 128u + (uint32_t)lane * 4u);
+    mx = warp_sum(fmaf(bf_lo(wq), bf_lo(wk), bf_hi(wq) * bf_hi(wk))) * sl2;
+    if (rl == 0) pvec[Tp] = mx;
+#pragma unroll 1
+    for (int j = rl; j < Tp; j += 128) {  // rolled on purpose (code size)
+      const float sj = dot_rows2(sK, j, sQ, Tp) * sl2;
+      pvec[j] = sj;
+      mx = fmaxf(mx, sj);
+    }
+  }
+  float2 se = make_float2(-INFINITY, -INFINITY);
+  {
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      const int r = t * 128 + rl;
+      const float v = r < Tp ? dot_rows2(sQ, r, sK, Tp) * sl2 : -INFINITY;
+      if (t == 0) se.x = v; else se.y = v;
+    }
+  }
+  if (rl < 32) {
+    const uint32_t v2 = lds32(sV + (uint32_t)Tp * 128u + (uint32_t)rl * 4u);
+    vedge[2 * rl] = bf_lo(v2);
+    vedge[2 * rl + 1] = bf_hi(v2);
+  }
+  mx = warp_max_f(mx);
+  if (lane == 0) red[q] = mx;
+  asm volatile("bar.sync 2, 128;" ::: "memory");
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float l = 0.f;
+#pragma unroll 1
+  for (int j = rl; j < T; j += 128) {
+    const float pj = ex2f(pvec[j] - mx);
+    pvec[j] = pj;
+    l += pj;
+  }
+  l = warp_sum(l);
+  if (lane == 0) red[4 + q] = l;
+  asm volatile("bar.sync 2, 128;" ::: "memory");
+  l = (red[4] + red[5]) + (red[6] + red[7]);
+  // O_e[d] = sum_j p_j V[j][d]: warp q takes the keys j = q (mod 4); lane owns d = 2 lane, 2 lane + 1 (one 32-bit word of a V row)
+  const uint32_t vcol = ((uint32_t)(lane >> 2) << 4), vin = (uint32_t)(lane & 3) << 2;
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+  int j = q;
+#pragma unroll 4
+  for (; j + 4 < T; j += 8) {
+    const uint32_t va = lds32(sV + (uint32_t)j * 128u + (vcol ^ ((uint32_t)(j & 7) << 4)) + vin);
+    const uint32_t vb = lds32(sV + (uint32_t)(j + 4) * 128u + (vcol ^ ((uint32_t)((j + 4) & 7) << 4)) + vin);
+    const float pa = pvec[j], pb = pvec[j + 4];
+    o0 = fmaf(pa, bf_lo(va), o0); o1 = fmaf(pa, bf_hi(va), o1);
+    o2 = fmaf(pb, bf_lo(vb), o2); o3 = fmaf(pb, bf_hi(vb), o3);
+  }
+  if (j < T) {
+    const uint32_t va = lds32(sV + (uint32_t)j * 128u + (vcol ^ ((uint32_t)(j & 7) << 4)) + vin);
+    o0 = fmaf(pvec[j], bf_lo(va), o0); o1 = fmaf(pvec[j], bf_hi(va), o1);
+  }
+  part[q * 32 + lane] = make_float2(o0 + o2, o1 + o3);
+  asm volatile("bar.sync 2, 128;" ::: "memory");
+  if (q == 0) {
+    const float2 a0 = part[lane], a1 = part[32 + lane], a2 = part[64 + lane], a3 = part[96 + lane];
+    const float inv = __fdividef(1.f, l);
+    reinterpret_cast<uint32_t*>(ctx_row)[lane] = pack_bf2(((a0.x + a1.x) + (a2.x + a3.x)) * inv, ((a0.y + a1.y) + (a2.y + a3.y)) * inv);
+    if (lane == 0) *lse_out = mx * (1.f / LOG2E_F) + logf(l);
+  }
+  return se;
+}
+
+// time-line probe of the persistent kernel: CTA 0, its third item (warm caches, steady state)
+#ifdef CG_ATTN_TRACE
+#define TRF(slot, idx, ev)                                                                                   \
+  do {                                                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0 && it == 2 && (threadIdx.x & 31) == 0)                         \
+      p.trace[(((slot) * 64 + (idx)) << 3) + (ev)] = clock64();                                              \
+  } while (0)
+#else
+#define TRF(slot, idx, ev) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(AT_THREADS, 1)
     attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKVtail, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   cg_griddep_launch();
-  const int T = p.T, D = p.heads * 64;
-  const int h = blockIdx.x, n = blockIdx.y;
+  const int T = p.T, heads = p.heads, D = heads * 64;
+  const int edge = p.edge, Tp = T - edge;  // Tp tokens go through the tensor-core pipeline; with edge = 1 token Tp is handled on CUDA cores
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntiles = p.ntiles, nblk = p.nblk;
-  const uint32_t opb = (uint32_t)((nblk - 1) * 64 + p.tail_rows) * 128u;
+  const int ntiles = p.ntiles, nblk = p.nblk, nblk_ld = p.nblk_ld;
+  const int G = ntiles * nblk, nitems = p.nitems;
+  const uint32_t opb = (uint32_t)((nblk_ld - 1) * 64 + p.ld_tail) * 128u;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sOp0 = base;                          // Q, K, V
-  const uint32_t sStage = base + 3 * opb;              // 4 x [128 x 64] bf16 P tiles
+  const uint32_t sQ = base, sK = base + opb, sV0 = base + 2 * opb;  // Q, K, V[2]
+  const uint32_t sStage = base + 4 * opb;                            // 4 x [128 x 64] bf16 P tiles
   const uint32_t sF = sStage + 4 * TILE_BYTES;
   float* fscr = reinterpret_cast<float*>(smem_raw + (sF - smem_u32(smem_raw)));
-  float* sm = fscr;         // [3][2][128] reference maxima (log2 units) per tile and warpgroup
-  float* sl = fscr + 768;   // [3][2][128] partial row sums
-  float* nscr = fscr + 1536;  // [2][64]: scores of a 1-row tile, spread over the lanes of the warp that owns the row
-  FBars bars{sF + (1536 + 128) * 4};
-  const int row0 = n * T;
-  const int G = ntiles * nblk;
+  float* sm = fscr;           // [4 slots][4 uses][128] reference maxima (log2 units) of a warpgroup's share of a tile
+  float* sl = fscr + 2048;    // [4 slots][4 uses][128] partial row sums
+  float* pvec = fscr + 4096;  // edge scratch: softmax numerators of the edge query row [288], reductions [8 + 256], v_e [64]
+  FBars bars{sF + FWD_FLOATS * 4};
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
@@ -770,59 +952,76 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     for (int b = 0; b < 4; ++b) {
       mbar_init(bars.sfull(b), 1); mbar_init(bars.sfree(b), 4); mbar_init(bars.pready(b), 4); mbar_init(bars.pfree(b), 1);
       mbar_init(bars.accfull(b), 1); mbar_init(bars.accfree(b), 4);
+      mbar_init(bars.mready(b, 0), 4); mbar_init(bars.mready(b, 1), 4);
     }
-    for (int t = 0; t < 3; ++t) mbar_init(bars.lready(t), 8);
-    for (int o = 0; o < 3; ++o)
-      for (int k = 0; k < MAX_BLK; ++k) mbar_init(bars.op(o, k), 1);
+    for (int k = 0; k < MAX_BLK; ++k) { mbar_init(bars.opq(k), 1); mbar_init(bars.opk(k), 1); mbar_init(bars.opv(0, k), 1); mbar_init(bars.opv(1, k), 1); }
+    mbar_init(bars.qkfree(), 6);
+    mbar_init(bars.vfree(0), 5);
+    mbar_init(bars.vfree(1), 5);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    cg_griddep_wait();  // the loads below read the predecessor's output
-    auto load = [&](int o, int blk) {
-      const bool tail = blk == nblk - 1;
-      const uint32_t bar = bars.op(o, blk);
-      mbar_arrive_expect_tx(bar, (uint32_t)(tail ? p.tail_rows : 64) * 128u);
-      tma_load_2d(sOp0 + o * opb + blk * BLK_BYTES, tail ? &tmQKVtail : &tmQKV, bar, o * D + h * 64, row0 + blk * 64);
-    };
-    const int first = nblk < 2 ? nblk : 2;
-    load(1, 0);
-    for (int k = 0; k < first; ++k) load(0, k);
-    load(2, 0);
-    for (int k = 1; k < nblk; ++k) { load(1, k); load(2, k); }
-    for (int k = first; k < nblk; ++k) load(0, k);
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  cg_griddep_wait();
+  cg_griddep_wait();  // everything below reads the predecessor's output or overwrites its input
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars.tmem_slot()) : "memory");
-  TR(warp, 63, 2);
 
-  if (warp < 3) {
-    // ================= MMA issuers (warp-converged loops, elected lane): warp 0 / 1 = S of the even / odd blocks, warp 2 = O += P V
+  if (warp == 3) {
+    // ================= TMA producer: Q / K single buffered (reloaded when the item's last S MMA and edge reads are done), V double buffered
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
+        const int n = w / heads, h = w - n * heads, row0 = n * T, vb = it & 1;
+        auto load = [&](uint32_t dst0, uint32_t bar, int col, int blk) {
+          const bool tail = blk == nblk_ld - 1;
+          mbar_arrive_expect_tx(bar, (uint32_t)(tail ? p.ld_tail : 64) * 128u);
+          tma_load_2d(dst0 + blk * BLK_BYTES, tail ? &tmQKVtail : &tmQKV, bar, col, row0 + blk * 64);
+        };
+        const int qc = h * 64, kc = D + h * 64, vc = 2 * D + h * 64;
+        const uint32_t sVb = sV0 + vb * opb;
+        // rolled loops on purpose (code size).  V first: its buffer has been free for a whole item, while Q / K have to wait for the
+        // previous item's last S MMA
+        if (it >= 2) mbar_wait(bars.vfree(vb), (uint32_t)((it >> 1) - 1) & 1u);  // item it - 2 has left this V buffer
+#pragma unroll 1
+        for (int k = 0; k < nblk_ld; ++k) load(sVb, bars.opv(vb, k), vc, k);
+        if (it >= 1) mbar_wait(bars.qkfree(), (uint32_t)(it - 1) & 1u);           // item it - 1 has left Q and K
+#pragma unroll 1
+        for (int k = 0; k < nblk_ld; ++k) {
+          load(sK, bars.opk(k), kc, k);
+          load(sQ, bars.opq(k), qc, k);
+        }
+      }
+    }
+  } else if (warp < 2) {
+    // ================= S issuers (warp-converged loops, elected lane): warp = parity of the running block index
     const uint32_t elected = elect_one();
-    uint32_t loaded = 0;
-    auto need = [&](int o, int blk) {
-      const uint32_t bit = 1u << (o * MAX_BLK + blk);
-      if (!(loaded & bit)) { mbar_wait(bars.op(o, blk), 0); loaded |= bit; }
-    };
-    const uint32_t id_full = idesc_bf16(64, false), id_tail = idesc_bf16(p.tail_rows, false), id_acc = idesc_bf16(64, true);
-    if (warp < 2) {
-      int tile = 0, blk = warp;  // block g = warp, warp + 2, ...
+    const uint32_t id_full = idesc_bf16(64, false), id_tail = idesc_bf16(p.tail_rows, false);
+    int it = 0, gg0 = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it, gg0 += G) {
+      const uint32_t opar = (uint32_t)it & 1u;
+      uint32_t loaded = 0;  // bit blk: Q block seen complete, bit 8 + blk: K block
+      auto need = [&](uint32_t bar, uint32_t bit) {
+        if (!(loaded & bit)) { mbar_wait(bar, opar); loaded |= bit; }
+      };
+      int g = ((gg0 & 1) == warp) ? 0 : 1;
+      int tile = 0, blk = g;
       while (blk >= nblk) { blk -= nblk; ++tile; }
-      for (int g = warp; g < G; g += 2) {
-        const int b = g & 3;
-        need(0, 2 * tile);
-        if (2 * tile + 1 < nblk) need(0, 2 * tile + 1);
-        need(1, blk);
-        mbar_wait(bars.sfree(b), ((uint32_t)(g >> 2) & 1u) ^ 1u);
-        TR(warp, g, 0);
+      bool any = false;
+      for (; g < G; g += 2) {
+        const int gg = gg0 + g, b = gg & 3;
+        need(bars.opq(2 * tile), 1u << (2 * tile));
+        if (2 * tile + 1 < nblk) need(bars.opq(2 * tile + 1), 1u << (2 * tile + 1));
+        need(bars.opk(blk), 256u << blk);
+        mbar_wait(bars.sfree(b), ((uint32_t)(gg >> 2) & 1u) ^ 1u);
+        TRF(warp, g, 0);
         tcgen05_fence_after();
         const uint32_t d_s = tmem_base + (uint32_t)(b * 64);
-        const uint64_t ad = make_smem_desc(sOp0 + tile * TILE_BYTES), bd = make_smem_desc(sOp0 + opb + blk * BLK_BYTES);
+        const uint64_t ad = make_smem_desc(sQ + tile * TILE_BYTES), bd = make_smem_desc(sK + blk * BLK_BYTES);
         const uint32_t idesc = blk == nblk - 1 ? id_tail : id_full;
         if (elected) {
 #pragma unroll
@@ -830,22 +1029,42 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
           umma_commit(bars.sfull(b));
         }
         __syncwarp();
-        TR(warp, g, 1);
+        TRF(warp, g, 1);
+        any = true;
         blk += 2;
         while (blk >= nblk) { blk -= nblk; ++tile; }
       }
-    } else {
+      // a parity wait is only sound for a waiter that sees EVERY phase: with an odd block count the blocks (and operand barriers) this
+      // warp needs alternate from item to item, so it also observes the ones it did not need
+#pragma unroll 1
+      for (int k = 0; k < nblk_ld; ++k) { need(bars.opq(k), 1u << k); need(bars.opk(k), 256u << k); }
+      if (elected) {  // this warp is done with Q and K of the item
+        if (any) umma_commit(bars.qkfree());
+        else mbar_arrive(bars.qkfree());
+      }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    // ================= P V issuer
+    const uint32_t elected = elect_one();
+    const uint32_t id_acc = idesc_bf16(64, true);
+    uint32_t accpar = 0;  // bit a: parity of the use count of accumulator slot a
+    int it = 0, gg0 = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it, gg0 += G) {
+      const int vb = it & 1;
+      const uint32_t vpar = (uint32_t)(it >> 1) & 1u, sVb = sV0 + vb * opb;
+      uint32_t loaded = 0;
       int tile = 0, blk = 0;
       for (int g = 0; g < G; ++g) {
-        const int pb = g & 3, wg = g & 1, a = 2 * wg + (tile & 1);
+        const int gg = gg0 + g, pb = gg & 3, wg = gg & 1, a = 2 * wg + (tile & 1);
         const bool first = blk < 2, last = blk + 2 >= nblk;  // first / last block of THIS warpgroup in the tile
-        need(2, blk);
-        mbar_wait(bars.pready(pb), (uint32_t)(g >> 2) & 1u);
-        TR(warp, g, 0);
-        if (first) mbar_wait(bars.accfree(a), ((uint32_t)(tile >> 1) & 1u) ^ 1u);
+        if (!(loaded & (1u << blk))) { mbar_wait(bars.opv(vb, blk), vpar); loaded |= 1u << blk; }
+        mbar_wait(bars.pready(pb), (uint32_t)(gg >> 2) & 1u);
+        TRF(warp, g, 0);
+        if (first) mbar_wait(bars.accfree(a), ((accpar >> a) & 1u) ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_acc = tmem_base + 256u + (uint32_t)(a * 64);
-        const uint64_t ad = make_smem_desc(sStage + pb * TILE_BYTES), bd = make_smem_desc(sOp0 + 2 * opb + blk * BLK_BYTES);
+        const uint64_t ad = make_smem_desc(sStage + pb * TILE_BYTES), bd = make_smem_desc(sVb + blk * BLK_BYTES);
         if (elected) {
           if (blk != nblk - 1) {
 #pragma unroll
@@ -858,161 +1077,114 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
           if (last) umma_commit(bars.accfull(a));
         }
         __syncwarp();
-        TR(warp, g, 1);
+        TRF(warp, g, 1);
+        if (last) accpar ^= 1u << a;
         if (++blk == nblk) { blk = 0; ++tile; }
       }
+      if (elected) umma_commit(bars.vfree(vb));  // this V buffer may be refilled once the item's last P V MMA has completed
+      __syncwarp();
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp < 12) {
     // ================= softmax warpgroups
     const int wg = (warp - 4) >> 2;
     const int q = warp & 3;
     const int rl = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = p.scale * LOG2E_F;
-    const int tail_cols = T - (nblk - 1) * 64, tail_cols16 = p.tail_rows;
-    const uint32_t srow = (uint32_t)rl * 128u, sx = (uint32_t)(rl & 7);
-    const uint32_t shalf0 = srow + ((0u ^ (sx & 4u)) << 4), shalf1 = srow + ((4u ^ (sx & 4u)) << 4);
-    const uint32_t so0 = ((0u ^ (sx & 3u)) << 4), so1 = ((1u ^ (sx & 3u)) << 4), so2 = ((2u ^ (sx & 3u)) << 4), so3 = ((3u ^ (sx & 3u)) << 4);
-    float mref = -INFINITY, lsum = 0.f;  // running reference maximum (log2 units) and row sum of this warpgroup in the current tile
-    int cur_tile = -1, pub = 0;          // tile the state belongs to; tiles already published to the epilogue
-    auto publish_until = [&](int t_end) {
-      while (pub < t_end) {
-        const bool mine = pub == cur_tile;
-        sm[(pub * 2 + wg) * 128 + rl] = mine ? mref : -INFINITY;
-        sl[(pub * 2 + wg) * 128 + rl] = mine ? lsum : 0.f;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars.lready(pub));
-        ++pub;
-      }
-    };
-    int tile = 0, blk = wg;
-    while (blk >= nblk) { blk -= nblk; ++tile; }
-    for (int g = wg; g < G; g += 2) {
-      const bool first = tile != cur_tile;
-      if (first) { publish_until(tile); cur_tile = tile; }
-      const bool wvalid = tile * 128 + q * 32 < T;
-      const bool rvalid = tile * 128 + rl < T;
-      const bool tail = blk == nblk - 1;
-      const int b = g & 3;                 // S buffer and staging buffer
-      const uint32_t use = (uint32_t)(g >> 2);
-      mbar_wait(bars.sfull(b), use & 1u);
-      TR(warp, g, 1);
-      tcgen05_fence_after();
-      if (!wvalid) {
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars.sfree(b));
-        mbar_wait(bars.pfree(b), (use & 1u) ^ 1u);  // stay in step with the barrier phases (see the backward kernel)
-      } else if (T - tile * 128 == 1) {
-        // ---- 1-row tile (T = 128 k + 1: the ViT-L/14 sequence 257): a thread-per-row pass would cost the warp a full block of MUFU issue
-        // for a single lane.  Lane 0 fetches the row from TMEM and hands it to the warp through shared memory: two columns per lane.
-        uint32_t sv[64];
-        const uint32_t t_s = t_lane + (uint32_t)(b * 64);
-        const int ncols = tail ? tail_cols : 64;
-        tmem_ld32(t_s, sv);
-        tmem_ld32(t_s + 32u, sv + 32);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars.sfree(b));
-        float* scr = nscr + wg * 64;
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) reinterpret_cast<uint4*>(scr)[j] = make_uint4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
-        }
-        __syncwarp();
-        const bool va = lane < ncols, vb = lane + 32 < ncols;
-        const float s_a = va ? scr[lane] * sl2 : -INFINITY, s_b = vb ? scr[lane + 32] * sl2 : -INFINITY;
-        __syncwarp();
-        const float bm = warp_max_f(fmaxf(s_a, s_b));
-        if (first) {
-          mref = bm;
-          lsum = 0.f;
-        } else if (bm > mref + RESCALE_LOG2) {  // warp-uniform
-          const int pbp = (g - 2) & 3;
-          mbar_wait(bars.pfree(pbp), (uint32_t)((g - 2) >> 2) & 1u);
-          tcgen05_fence_after();
-          const float f = ex2f(mref - bm);
-          const uint32_t t_o = t_lane + 256u + (uint32_t)((2 * wg + (tile & 1)) * 64);
-#pragma unroll
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t o[32];
-            tmem_ld32(t_o + (uint32_t)c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
-            tmem_st32(t_o + (uint32_t)c, o);
-          }
-          tmem_st_wait();
+    const int tail_cols = Tp - (nblk - 1) * 64, tail_cols16 = p.tail_rows;
+    const uint32_t sx = (uint32_t)(rl & 7) << 4;  // 128B swizzle of this thread's row of a staged tile: 16-byte chunk c sits at (c << 4) ^ sx
+    uint32_t wuse0 = 0, wuse1 = 0;  // uses of this warpgroup's two accumulator slots (tile parity 0 / 1)
+    int it = 0, gg0 = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it, gg0 += G) {
+      float mref = -INFINITY, lsum = 0.f;  // running reference maximum (log2 units) and row sum of this warpgroup in the current tile
+      int cur_tile = -1;
+      int g = ((gg0 & 1) == wg) ? 0 : 1;
+      int tile = 0, blk = g;
+      while (blk >= nblk) { blk -= nblk; ++tile; }
+      for (; g < G; g += 2) {
+        const int gg = gg0 + g;
+        const bool first = tile != cur_tile;
+        cur_tile = tile;
+        const bool wvalid = tile * 128 + q * 32 < Tp;
+        const bool rvalid = tile * 128 + rl < Tp;
+        const bool tail = blk == nblk - 1, last_in_tile = blk + 2 >= nblk;
+        const int b = gg & 3;                 // S buffer and staging buffer
+        const uint32_t use = (uint32_t)(gg >> 2);
+        mbar_wait(bars.sfull(b), use & 1u);
+        TRF(warp, g, 1);
+        tcgen05_fence_after();
+        if (!wvalid) {
           tcgen05_fence_before();
-          lsum *= f;
-          mref = bm;
-        }
-        const float p_a = ex2f(s_a - mref), p_b = ex2f(s_b - mref);  // ex2(-inf) = 0 for the masked columns
-        lsum += warp_sum(p_a + p_b);
-        mbar_wait(bars.pfree(b), (use & 1u) ^ 1u);  // staging buffer free again
-        const uint32_t srow0 = sStage + b * TILE_BYTES;  // row 0 of the tile: no swizzle permutation
-        st_shared_b16(srow0 + (uint32_t)lane * 2u, p_a);
-        st_shared_b16(srow0 + 64u + (uint32_t)lane * 2u, p_b);
-      } else {
-        uint32_t sv[64], w[16];
-        const uint32_t t_s = t_lane + (uint32_t)(b * 64);
-        const int ncols16 = tail ? tail_cols16 : 64;
-        tmem_ld32(t_s, sv);
-        if (ncols16 > 32) tmem_ld32(t_s + 32u, sv + 32);
-        tmem_ld_wait();
-        TR(warp, g, 0);
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars.sfree(b));
-        // block maximum over the valid columns
-        float bm = -INFINITY;
-        if (!tail) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) bm = fmaxf(bm, __uint_as_float(sv[j]));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars.sfree(b));
+          mbar_wait(bars.pfree(b), (use & 1u) ^ 1u);  // stay in step with the barrier phases (see the backward kernel)
         } else {
+          // Register budget (512 threads x 128 registers, and the local memory of a spill lives in L2 here: shared memory leaves ~28 KB of
+          // L1): the block is read from TMEM TWICE.  Pass 1 takes the block maximum over both 32-column halves; the first half is then
+          // dropped, the second half is exponentiated and staged, the first half is fetched again (a TMEM read costs a few dozen cycles).
+          uint32_t sa[32], sb[32], w[16];
+          const uint32_t t_s = t_lane + (uint32_t)(b * 64);
+          tmem_ld32(t_s, sa);
+          tmem_ld32(t_s + 32u, sb);  // (a tail block narrower than 32 columns leaves stale columns here: masked below)
+          tmem_ld_wait();
+          TRF(warp, g, 0);
+          // block maximum over the valid columns
+          float bm = -INFINITY;
+          if (!tail) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if (j < tail_cols) bm = fmaxf(bm, __uint_as_float(sv[j]));
-        }
-        bm *= sl2;
-        TR(warp, g, 4);
-        if (first) {
-          mref = bm;
-          lsum = 0.f;
-        } else {
-          const bool grow = rvalid && bm > mref + RESCALE_LOG2;
-          if (__any_sync(0xffffffffu, grow)) {
-            // the reference moves: rescale this warpgroup's accumulator.  Its previous block (g - 2) must have left the tensor pipe.
-            const int pbp = (g - 2) & 3;
-            mbar_wait(bars.pfree(pbp), (uint32_t)((g - 2) >> 2) & 1u);
-            tcgen05_fence_after();
-            const float f = grow ? ex2f(mref - bm) : 1.f;
-            const uint32_t t_o = t_lane + 256u + (uint32_t)((2 * wg + (tile & 1)) * 64);
+            for (int j = 0; j < 32; ++j) bm = fmaxf(bm, fmaxf(__uint_as_float(sa[j]), __uint_as_float(sb[j])));
+          } else {
 #pragma unroll
-            for (int c = 0; c < 64; c += 32) {
-              uint32_t o[32];
-              tmem_ld32(t_o + (uint32_t)c, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
-              tmem_st32(t_o + (uint32_t)c, o);
+            for (int j = 0; j < 32; ++j) {
+              if (j < tail_cols) bm = fmaxf(bm, __uint_as_float(sa[j]));
+              if (32 + j < tail_cols) bm = fmaxf(bm, __uint_as_float(sb[j]));
             }
-            tmem_st_wait();
-            tcgen05_fence_before();
-            lsum *= f;
-            if (grow) mref = bm;
           }
-        }
-        bool waited = false;
+          bm *= sl2;
+          TRF(warp, g, 4);
+          if (first) {
+            mref = bm;
+            lsum = 0.f;
+          } else {
+            const bool grow = rvalid && bm > mref + RESCALE_LOG2;
+            if (__any_sync(0xffffffffu, grow)) {
+              // the reference moves: rescale this warpgroup's accumulator.  Its previous block (gg - 2) must have left the tensor pipe.
+              const int pbp = (gg - 2) & 3;
+              mbar_wait(bars.pfree(pbp), (uint32_t)((gg - 2) >> 2) & 1u);
+              tcgen05_fence_after();
+              const float f = grow ? ex2f(mref - bm) : 1.f;
+              const uint32_t t_o = t_lane + 256u + (uint32_t)((2 * wg + (tile & 1)) * 64);
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          if (hlf * 32 < ncols16) {
+              for (int c = 0; c < 64; c += 32) {  // (sa is dead here: it is fetched again below)
+                tmem_ld32(t_o + (uint32_t)c, sa);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sa[j] = __float_as_uint(__uint_as_float(sa[j]) * f);
+                tmem_st32(t_o + (uint32_t)c, sa);
+              }
+              tmem_st_wait();
+              tcgen05_fence_before();
+              lsum *= f;
+              if (grow) mref = bm;
+            }
+          }
+          bool waited = false;
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const int hlf = 1 - pass;  // second half first (it is still in registers), then the first half again
+            if (pass == 1) {
+              tmem_ld32(t_s, sa);
+              tmem_ld_wait();
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bars.sfree(b));  // every TMEM read of this block has completed
+            }
+            const uint32_t* sv = hlf ? sb : sa;
             float a0 = 0.f, a1 = 0.f;  // independent partial sums
             if (!tail) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const float p0 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j]), sl2, -mref)), p1 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j + 1]), sl2, -mref));
+                const float p0 = ex2f(fmaf(__uint_as_float(sv[2 * j]), sl2, -mref)), p1 = ex2f(fmaf(__uint_as_float(sv[2 * j + 1]), sl2, -mref));
                 a0 += p0;
                 a1 += p1;
                 w[j] = pack_bf2(p0, p1);
@@ -1020,7 +1192,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                float p0 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j]), sl2, -mref)), p1 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j + 1]), sl2, -mref));
+                float p0 = ex2f(fmaf(__uint_as_float(sv[2 * j]), sl2, -mref)), p1 = ex2f(fmaf(__uint_as_float(sv[2 * j + 1]), sl2, -mref));
                 if (hlf * 32 + 2 * j >= tail_cols) p0 = 0.f;
                 if (hlf * 32 + 2 * j + 1 >= tail_cols) p1 = 0.f;
                 a0 += p0;
@@ -1029,76 +1201,117 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
               }
             }
             lsum += a0 + a1;
-            TR(warp, g, 5 + hlf);
+            TRF(warp, g, 5 + hlf);
             if (!waited) { mbar_wait(bars.pfree(b), (use & 1u) ^ 1u); waited = true; }  // staging buffer free again
-            if (hlf == 0) TR(warp, g, 7);
-            const uint32_t hb = sStage + b * TILE_BYTES + (hlf ? shalf1 : shalf0);
-            st_shared_v4(hb + so0, w[0], w[1], w[2], w[3]);
-            st_shared_v4(hb + so1, w[4], w[5], w[6], w[7]);
-            st_shared_v4(hb + so2, w[8], w[9], w[10], w[11]);
-            st_shared_v4(hb + so3, w[12], w[13], w[14], w[15]);
+            const uint32_t hb = sStage + b * TILE_BYTES + (uint32_t)rl * 128u;
+            st_shared_v4(hb + (((uint32_t)(hlf * 64)) ^ sx), w[0], w[1], w[2], w[3]);
+            st_shared_v4(hb + (((uint32_t)(hlf * 64 + 16)) ^ sx), w[4], w[5], w[6], w[7]);
+            st_shared_v4(hb + (((uint32_t)(hlf * 64 + 32)) ^ sx), w[8], w[9], w[10], w[11]);
+            st_shared_v4(hb + (((uint32_t)(hlf * 64 + 48)) ^ sx), w[12], w[13], w[14], w[15]);
           }
         }
+        if (last_in_tile) {
+          // this warpgroup's share of the tile is complete: hand its reference maximum and row sum to the epilogue (ring of 4 per
+          // slot: the staging depth lets a warpgroup run at most two uses of a slot ahead of the epilogue)
+          const int tp = tile & 1, a = 2 * wg + tp;
+          const uint32_t u = tp ? wuse1 : wuse0;
+          if (wvalid) {
+            sm[(a * 4 + (int)(u & 3u)) * 128 + rl] = mref;
+            sl[(a * 4 + (int)(u & 3u)) * 128 + rl] = lsum;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars.mready(a, u & 1u));
+          if (tp) wuse1 = u + 1; else wuse0 = u + 1;
+        }
+        TRF(warp, g, 2);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.pready(b));
+        TRF(warp, g, 3);
+        blk += 2;
+        while (blk >= nblk) { blk -= nblk; ++tile; }
       }
-      TR(warp, g, 2);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars.pready(b));
-      TR(warp, g, 3);
-      blk += 2;
-      while (blk >= nblk) { blk -= nblk; ++tile; }
     }
-    publish_until(ntiles);
-  } else if (warp >= 12) {
-    // ================= epilogue: merge the two warpgroups' partial results of a tile -> ctx (bf16), lse
+  } else {
+    // ================= epilogue warps: edge token, then merge the two warpgroups' partial results of every tile -> ctx (bf16), lse
     const int q = warp & 3;
     const int rl = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int tile = 0; tile < ntiles; ++tile) {
-      const int tp = tile & 1;
-      const uint32_t par = (uint32_t)((tile >> 1) & 1);
-      // with a single block per tile only warpgroup (tile * nblk) & 1 takes part
-      const bool has0 = nblk > 1 || ((tile * nblk) & 1) == 0, has1 = nblk > 1 || ((tile * nblk) & 1) == 1;
-      mbar_wait(bars.lready(tile), 0);
-      if (has0) mbar_wait(bars.accfull(0 + tp), par);
-      if (has1) mbar_wait(bars.accfull(2 + tp), par);
-      TR(warp, tile, 0);
-      tcgen05_fence_after();
-      const int row = tile * 128 + rl;
-      if (tile * 128 + q * 32 < T) {
-        const float m0 = sm[(tile * 2 + 0) * 128 + rl], m1 = sm[(tile * 2 + 1) * 128 + rl];
-        const float l0 = sl[(tile * 2 + 0) * 128 + rl], l1 = sl[(tile * 2 + 1) * 128 + rl];
-        const float M = fmaxf(m0, m1);
-        const float f0 = has0 ? ex2f(m0 - M) : 0.f, f1 = has1 ? ex2f(m1 - M) : 0.f;
-        const float L = l0 * f0 + l1 * f1;
-        const float g0 = f0 / L, g1 = f1 / L;
-        __nv_bfloat16* dst = p.ctx + ((long long)(row0 + row)) * D + h * 64;
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t v0[32], v1[32], w[16];
-          if (has0) tmem_ld32(t_lane + 256u + (uint32_t)((0 + tp) * 64 + c), v0);
-          if (has1) tmem_ld32(t_lane + 256u + (uint32_t)((2 + tp) * 64 + c), v1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a0 = (has0 ? __uint_as_float(v0[2 * j]) * g0 : 0.f) + (has1 ? __uint_as_float(v1[2 * j]) * g1 : 0.f);
-            const float a1 = (has0 ? __uint_as_float(v0[2 * j + 1]) * g0 : 0.f) + (has1 ? __uint_as_float(v1[2 * j + 1]) * g1 : 0.f);
-            w[j] = pack_bf2(a0, a1);
-          }
-          if (row < T) { st256g(dst + c, w); st256g(dst + c + 16, w + 8); }
-        }
-        if (row < T) p.lse[((long long)n * p.heads + h) * T + row] = M * (1.f / LOG2E_F) + logf(L);
+    const float sl2 = p.scale * LOG2E_F;
+    const float* vedge = pvec + 552;                          // [64] v_e as floats (written by fwd_edge_token)
+    uint32_t euse = 0;  // 4 bits per accumulator slot: its use count (mod 16)
+    int it = 0, gg0 = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it, gg0 += G) {
+      const int n = w / heads, h = w - n * heads, row0 = n * T, vb = it & 1;
+      const uint32_t opar = (uint32_t)it & 1u, vpar = (uint32_t)(it >> 1) & 1u, sVb = sV0 + vb * opb;
+      float se0 = -INFINITY, se1 = -INFINITY;  // edge key scores of this thread's row in tile 0 / 1 (log2 units)
+      TRF(warp, 62, 0);
+      if (edge) {
+        for (int b = 0; b < nblk_ld; ++b) { mbar_wait(bars.opk(b), opar); mbar_wait(bars.opv(vb, b), vpar); mbar_wait(bars.opq(b), opar); }
+        TRF(warp, 61, 0);
+        const float2 se = fwd_edge_token(sQ, sK, sVb, Tp, sl2, pvec, p.ctx + ((long long)(row0 + Tp)) * D + h * 64, p.lse + ((long long)n * heads + h) * T + Tp);
+        se0 = se.x;
+        se1 = se.y;
+        TRF(warp, 61, 1);
       }
-      tcgen05_fence_before();
+      // this role no longer reads Q, K, V of the item from shared memory (the barrier arrival orders the reads above before the refill)
       __syncwarp();
-      if (lane == 0) {
-        if (has0) mbar_arrive(bars.accfree(0 + tp));
-        if (has1) mbar_arrive(bars.accfree(2 + tp));
+      if (lane == 0) { mbar_arrive(bars.qkfree()); mbar_arrive(bars.vfree(vb)); }
+      for (int tile = 0; tile < ntiles; ++tile) {
+        const int tp = tile & 1, a0 = tp, a1 = 2 + tp;
+        // with a single block per tile only warpgroup (running block index) & 1 takes part
+        const int ggt = gg0 + tile * nblk;
+        const bool has0 = nblk > 1 || (ggt & 1) == 0, has1 = nblk > 1 || (ggt & 1) == 1;
+        const uint32_t u0 = (euse >> (4 * a0)) & 15u, u1 = (euse >> (4 * a1)) & 15u;
+        if (has0) { mbar_wait(bars.mready(a0, u0 & 1u), (u0 >> 1) & 1u); mbar_wait(bars.accfull(a0), u0 & 1u); }
+        if (has1) { mbar_wait(bars.mready(a1, u1 & 1u), (u1 >> 1) & 1u); mbar_wait(bars.accfull(a1), u1 & 1u); }
+        TRF(warp, tile, 0);
+        tcgen05_fence_after();
+        const int row = tile * 128 + rl;
+        if (tile * 128 + q * 32 < Tp) {
+          const float m0 = has0 ? sm[(a0 * 4 + (int)(u0 & 3u)) * 128 + rl] : -INFINITY, m1 = has1 ? sm[(a1 * 4 + (int)(u1 & 3u)) * 128 + rl] : -INFINITY;
+          const float l0 = has0 ? sl[(a0 * 4 + (int)(u0 & 3u)) * 128 + rl] : 0.f, l1 = has1 ? sl[(a1 * 4 + (int)(u1 & 3u)) * 128 + rl] : 0.f;
+          const float se = tile == 0 ? se0 : se1;  // -inf without an edge token (and for tiles >= 2, which only exist without one)
+          const float M = fmaxf(fmaxf(m0, m1), se);
+          const float f0 = has0 ? ex2f(m0 - M) : 0.f, f1 = has1 ? ex2f(m1 - M) : 0.f, fe = ex2f(se - M);
+          const float L = l0 * f0 + l1 * f1 + fe;
+          const float invL = __fdividef(1.f, L);
+          const float g0 = f0 * invL, g1 = f1 * invL, ge = fe * invL;
+          __nv_bfloat16* dst = p.ctx + ((long long)(row0 + row)) * D + h * 64;
+#pragma unroll
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t v0[32], v1[32], wv[16];
+            if (has0) tmem_ld32(t_lane + 256u + (uint32_t)(a0 * 64 + c), v0);
+            if (has1) tmem_ld32(t_lane + 256u + (uint32_t)(a1 * 64 + c), v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x0 = (has0 ? __uint_as_float(v0[2 * j]) * g0 : 0.f) + (has1 ? __uint_as_float(v1[2 * j]) * g1 : 0.f);
+              float x1 = (has0 ? __uint_as_float(v0[2 * j + 1]) * g0 : 0.f) + (has1 ? __uint_as_float(v1[2 * j + 1]) * g1 : 0.f);
+              if (edge) {
+                const float2 ve = *reinterpret_cast<const float2*>(vedge + c + 2 * j);  // broadcast read
+                x0 = fmaf(ge, ve.x, x0);
+                x1 = fmaf(ge, ve.y, x1);
+              }
+              wv[j] = pack_bf2(x0, x1);
+            }
+            if (row < Tp) { st256g(dst + c, wv); st256g(dst + c + 16, wv + 8); }
+          }
+          if (row < Tp) p.lse[((long long)n * heads + h) * T + row] = M * (1.f / LOG2E_F) + logf(L);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (has0) mbar_arrive(bars.accfree(a0));
+          if (has1) mbar_arrive(bars.accfree(a1));
+        }
+        if (has0) euse = (euse & ~(15u << (4 * a0))) | (((u0 + 1u) & 15u) << (4 * a0));
+        if (has1) euse = (euse & ~(15u << (4 * a1))) | (((u1 + 1u) & 15u) << (4 * a1));
+        TRF(warp, tile, 1);
       }
-      TR(warp, tile, 1);
+      TRF(warp, 62, 1);
     }
   }
-  TR(warp, 63, 3);
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -1108,6 +1321,39 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 }
 
 long long* g_trace = nullptr;
+
+// Pipeline / load geometry.  T = 64 m + 1 (ViT-L/14: 16 x 16 patches + class token = 257): the LAST token is taken out of the tensor-core pipeline ("edge"), which then sees only full 64-wide blocks and full 128-row
+// tiles; CG_ATTN_EDGE=0 keeps it in (A/B measurements, and the narrow-tile code paths stay tested).
+int edge_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CG_ATTN_EDGE");
+    v = e ? atoi(e) : 3;  // bit 0: forward, bit 1: backward
+  }
+  return v;
+}
+bool fwd_edge_enabled() { return (edge_env() & 1) != 0; }
+bool bwd_edge_enabled() { return (edge_env() & 2) != 0; }
+void set_geometry(AttnParams& p, int T, bool allow_edge) {
+  p.edge = (allow_edge && T > 1 && (T - 1) % 64 == 0) ? 1 : 0;
+  const int Tp = T - p.edge;
+  p.ntiles = (Tp + 127) / 128;
+  p.nblk = (Tp + 63) / 64;
+  p.tail_rows = ((Tp - (p.nblk - 1) * 64) + 15) & ~15;
+  p.nblk_ld = p.nblk + p.edge;
+  p.ld_tail = p.edge ? 16 : p.tail_rows;
+}
+
+int cg_num_sms() {
+  static int per_device[CG_MAX_DEVICES] = {};
+  const int dev = cg_device_index();
+  if (per_device[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    per_device[dev] = n > 0 ? n : CG_NUM_SMS;
+  }
+  return per_device[dev];
+}
 
 int tc_enabled() {
   static int enabled = -1;
@@ -1123,9 +1369,7 @@ int launch_attn_tc(const void* qkv, const void* dctx, int Nimg, int T, int heads
   AttnParams p = p0;
   p.T = T; p.heads = heads; p.scale = 0.125f;
   p.trace = g_trace;
-  p.ntiles = (T + 127) / 128;
-  p.nblk = (T + 63) / 64;
-  p.tail_rows = ((T - (p.nblk - 1) * 64) + 15) & ~15;
+  set_geometry(p, T, false);
   const int D = heads * 64;
   CUtensorMap tq, tqt, td, tdt;
   int rc = cg_make_tensor_map_bf16(&tq, qkv, (long long)Nimg * T, 3LL * D, 3LL * D, 64);
@@ -1161,24 +1405,24 @@ int cg_attention_fwd_tc(const void* qkv, int Nimg, int T, int heads, void* ctx, 
   p.lse = lse;
   p.T = T; p.heads = heads; p.scale = 0.125f;
   p.trace = g_trace;
-  p.ntiles = (T + 127) / 128;
-  p.nblk = (T + 63) / 64;
-  p.tail_rows = ((T - (p.nblk - 1) * 64) + 15) & ~15;
+  set_geometry(p, T, fwd_edge_enabled());
   const int D = heads * 64;
   CUtensorMap tq, tqt;
   int rc = cg_make_tensor_map_bf16(&tq, qkv, (long long)Nimg * T, 3LL * D, 3LL * D, 64);
   if (rc) return rc;
-  rc = cg_make_tensor_map_bf16(&tqt, qkv, (long long)Nimg * T, 3LL * D, 3LL * D, p.tail_rows);
+  rc = cg_make_tensor_map_bf16(&tqt, qkv, (long long)Nimg * T, 3LL * D, 3LL * D, p.ld_tail);
   if (rc) return rc;
-  const size_t opb = (size_t)((p.nblk - 1) * 64 + p.tail_rows) * 128;
-  const size_t smem = 1024 + 3 * opb + 4 * (size_t)TILE_BYTES + (1536 + 128) * 4 + FBARS_BYTES;
+  const size_t opb = (size_t)((p.nblk_ld - 1) * 64 + p.ld_tail) * 128;
+  const size_t smem = 1024 + 4 * opb + 4 * (size_t)TILE_BYTES + FWD_FLOATS * 4 + FBARS_BYTES;
+  p.nitems = Nimg * heads;
+  const int grid = p.nitems < cg_num_sms() ? p.nitems : cg_num_sms();  // persistent: one CTA per SM
   static size_t configured[CG_MAX_DEVICES] = {};
   const int dev = cg_device_index();
   if (smem > configured[dev]) {
     CG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dev] = smem;
   }
-  CG_CUDA(cg_launch_pdl(attn_fwd_tc_kernel, dim3(heads, Nimg), dim3(AT_THREADS), smem, s, tq, tqt, p));
+  CG_CUDA(cg_launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(AT_THREADS), smem, s, tq, tqt, p));
   return 0;
 }
 

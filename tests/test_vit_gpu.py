@@ -46,7 +46,10 @@ def test_layernorm_fwd_bwd(M, D, stride):
 
 
 @pytest.mark.parametrize("n,T,heads", [(3, 50, 2), (2, 197, 12), (1, 257, 16), (1, 577, 4), (5, 5, 2), (2, 64, 3), (2, 65, 1), (1, 128, 2), (1, 129, 2),
-                                       (2, 256, 2), (1, 272, 1), (3, 257, 4), (1, 16, 1), (2, 192, 2), (2, 193, 1)])
+                                       (2, 256, 2), (1, 272, 1), (3, 257, 4), (1, 16, 1), (2, 192, 2), (2, 193, 1),
+                                       # more (image, head) items than SMs: the persistent kernels walk several items per CTA and pipeline across
+                                       # them (even / odd block counts per item, with and without the edge token T = 64 m + 1)
+                                       (40, 257, 4), (64, 50, 3), (30, 129, 5), (50, 65, 3), (52, 100, 3), (38, 272, 4), (75, 197, 2), (150, 257, 3)])
 def test_attention_fwd_bwd(n, T, heads):
     """Default path: tcgen05/TMEM kernels (vit_attention_tc.cu) for T <= 272, mma.sync kernels beyond (T = 577)."""
     _lib = _lib_ops()
