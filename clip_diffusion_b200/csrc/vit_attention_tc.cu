@@ -182,58 +182,6 @@ __device__ __forceinline__ void load_row64(uint32_t buf, int r, float* f) {
   for (int c = 0; c < 8; ++c) unpack8(lds128(rowb + (((uint32_t)c ^ x) << 4)), f + 8 * c);
 }
 
-// Pipeline depths.  S (and dP) blocks: 4 x 64 TMEM columns in the forward, 3 x 128 in the backward (the accumulators need the
-// rest of the 512 columns); staging buffers: 4 x 16 KB in the forward, 2 x 32 KB (P^T and dS^T) in the backward.
-template <bool FWD> struct Depth { static constexpr int NSB = FWD ? 4 : 3, NPB = FWD ? 4 : 2; };
-
-// barrier block (8 bytes each)
-struct Bars {
-  uint32_t base;
-  __device__ __forceinline__ uint32_t sfull(int b) const { return base + 8u * b; }            // S (dP) block in TMEM buffer b          (tcgen05.commit)
-  __device__ __forceinline__ uint32_t sfree(int b) const { return base + 32u + 8u * b; }      // the owning warpgroup has read it        (4 warps)
-  __device__ __forceinline__ uint32_t pready(int b) const { return base + 64u + 8u * b; }     // staging buffer b is written             (4 warps)
-  __device__ __forceinline__ uint32_t pfree(int b) const { return base + 96u + 8u * b; }      // accumulator MMAs have consumed it       (tcgen05.commit)
-  __device__ __forceinline__ uint32_t accfull(int a) const { return base + 128u + 8u * a; }   // accumulator a is complete               (tcgen05.commit)
-  __device__ __forceinline__ uint32_t accfree(int a) const { return base + 152u + 8u * a; }   // epilogue has read it                    (4 warps)
-  __device__ __forceinline__ uint32_t lready(int t) const { return base + 176u + 8u * t; }    // forward: row sums of tile t are in smem (8 warps)
-  __device__ __forceinline__ uint32_t op(int o, int blk) const { return base + 200u + 8u * (o * MAX_BLK + blk); }  // operand o, 64-row block
-  __device__ __forceinline__ uint32_t tmem_slot() const { return base + 200u + 8u * (4 * MAX_BLK); }
-};
-constexpr uint32_t BARS_BYTES = 200 + 8 * 4 * MAX_BLK + 16;
-
-// The block stream.  Every role (the two MMA issuers, the two softmax warpgroups, the epilogue warps) walks the SAME enumeration,
-// so buffer indices and mbarrier parities are derived identically everywhere.
-//   backward: phase-major  (phase 0 = dQ with lane = query, phase 1 = dK/dV with lane = key) -> tile -> 64-wide block
-//   forward:  tile-major   tile -> pass (0 = row maximum, 1 = exponentials + O) -> block
-template <bool FWD>
-struct BlkIt {
-  int phase = 0, tile = 0, blk = 0;
-  int g = 0;       // running block index: warpgroup = g & 1, TMEM buffer = g % NSB
-  int s = 0;       // running index of the blocks that stage an operand (forward: pass-1 blocks only): staging buffer = s % NPB
-  int tcount = 0;  // running accumulator-tile index
-  __device__ __forceinline__ bool valid(int ntiles) const { return FWD ? tile < ntiles : phase < 2; }
-  __device__ __forceinline__ bool stages() const { return !FWD || phase == 1; }
-  __device__ __forceinline__ int sbuf() const { return g % Depth<FWD>::NSB; }
-  __device__ __forceinline__ uint32_t suse() const { return (uint32_t)(g / Depth<FWD>::NSB); }
-  __device__ __forceinline__ int pbuf() const { return s % Depth<FWD>::NPB; }
-  __device__ __forceinline__ uint32_t puse() const { return (uint32_t)(s / Depth<FWD>::NPB); }
-  // accumulator slot and its use count: forward / backward phase A alternate two slots; phase B (dV + dK = 128 columns) has one
-  __device__ __forceinline__ int acc() const { return (!FWD && phase == 1) ? 2 : (tcount & 1); }
-  __device__ __forceinline__ uint32_t ause() const { return (uint32_t)((!FWD && phase == 1) ? tile : (tcount >> 1)); }
-  __device__ __forceinline__ void next(int ntiles, int nblk) {
-    if (stages()) ++s;
-    ++g;
-    if (++blk < nblk) return;
-    blk = 0;
-    if (FWD) {
-      if (phase == 0) { phase = 1; } else { phase = 0; ++tile; ++tcount; }
-    } else {
-      ++tcount;
-      if (++tile == ntiles) { tile = 0; ++phase; }
-    }
-  }
-};
-
 struct AttnParams {
   int T, heads, ntiles, nblk, tail_rows;  // tiles / 64-wide blocks of the tensor-core pipeline; tail_rows: rows of its last block, rounded up to 16
   int nitems;                             // forward (persistent kernel): (image, head) items = Nimg * heads
@@ -246,538 +194,6 @@ struct AttnParams {
   __nv_bfloat16* dqkv;       // backward out [Nimg*T, 3D]
   long long* trace;          // debug: clock64() time line of CTA (0,0) (tools/trace_attn.py); nullptr in production
 };
-// time-line probe (compiled in with -DCG_ATTN_TRACE only): slot = role, idx = block, ev = event
-#ifdef CG_ATTN_TRACE
-#define TR(slot, idx, ev)                                                                                   \
-  do {                                                                                                      \
-    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == (gridDim.y >> 1) && (threadIdx.x & 31) == 0) /* a CTA of a later wave: warm instruction cache */                \
-      p.trace[(((slot) * 64 + (idx)) << 3) + (ev)] = clock64();                                             \
-  } while (0)
-#else
-#define TR(slot, idx, ev) do { } while (0)
-#endif
-
-__device__ __forceinline__ int blk_cols(const AttnParams& p, int blk) { return blk == p.nblk - 1 ? p.T - blk * 64 : 64; }
-__device__ __forceinline__ int blk_cols16(const AttnParams& p, int blk) { return blk == p.nblk - 1 ? p.tail_rows : 64; }
-
-// TMEM columns
-template <bool FWD> __device__ __forceinline__ uint32_t s_col(int sbuf) { return (uint32_t)(FWD ? sbuf * 64 : sbuf * 128); }
-template <bool FWD> __device__ __forceinline__ uint32_t acc_col(int a) { return FWD ? 256u + 64u * a : (a == 2 ? 384u : 384u + 64u * a); }
-
-// operands in shared memory: 0 = Q, 1 = K, 2 = V, 3 = dO
-template <bool FWD>
-__global__ void __launch_bounds__(AT_THREADS, 1)
-    attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKVtail, const __grid_constant__ CUtensorMap tmDO,
-                   const __grid_constant__ CUtensorMap tmDOtail, const AttnParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  cg_griddep_launch();
-  constexpr int NOPS = FWD ? 3 : 4;
-  constexpr int NSB = Depth<FWD>::NSB, NPB = Depth<FWD>::NPB;
-  constexpr uint32_t STAGE_BYTES = FWD ? TILE_BYTES : 2 * TILE_BYTES;  // backward phase B stages P^T and dS^T
-  const int T = p.T, D = p.heads * 64;
-  const int h = blockIdx.x, n = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t opb = (uint32_t)((p.nblk - 1) * 64 + p.tail_rows) * 128u;  // bytes per operand buffer (multiple of 2048)
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sOp0 = base;
-  const uint32_t sStage = base + NOPS * opb;                    // 1024-aligned; also absorbs the A-operand over-read of the last tile
-  const uint32_t sF = sStage + NPB * STAGE_BYTES;               // float scratch
-  float* fscr = reinterpret_cast<float*>(smem_raw + (sF - smem_u32(smem_raw)));
-  // forward: smax[2][128] (per warpgroup partial row maxima), sl[3][2][128] (tile, warpgroup: partial row sums), smf[3][128] (final row
-  // maxima per tile; T <= 272 -> <= 3 tiles, so nothing is ever overwritten while the epilogue may still read it)
-  // backward: nlse[320], delta[320]
-  constexpr uint32_t FSCR_FLOATS = FWD ? (256 + 768 + 384) : (640 + 256);  // backward: + [2][128] scratch of the 1-row tiles
-  Bars bars{sF + FSCR_FLOATS * 4};
-  const int row0 = n * T;  // first row of this image in the packed [Nimg*T, 3D] qkv matrix
-  const int ntiles = p.ntiles, nblk = p.nblk;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKVtail) : "memory");
-    if (!FWD) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDOtail) : "memory");
-    }
-    // backward: two issuer warps feed every block (S and dP) and two drain every staging buffer (dQ | dV and dK): their barriers count 2
-    constexpr uint32_t NISS = FWD ? 1 : 2;
-    for (int b = 0; b < 4; ++b) { mbar_init(bars.sfull(b), NISS); mbar_init(bars.sfree(b), 4); mbar_init(bars.pready(b), 4); mbar_init(bars.pfree(b), NISS); }
-    for (int a = 0; a < 3; ++a) { mbar_init(bars.accfull(a), NISS); mbar_init(bars.accfree(a), 4); mbar_init(bars.lready(a), 8); }
-    for (int o = 0; o < 4; ++o)
-      for (int k = 0; k < MAX_BLK; ++k) mbar_init(bars.op(o, k), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    cg_griddep_wait();  // the loads below read the predecessor's output
-    // ================= TMA producer: every operand block once, in the order the MMA issuers need them; issued before the CTA-wide
-    // sync below (only this thread has touched the barriers so far) so the loads overlap the TMEM allocation
-    auto load = [&](int o, int blk) {
-      const bool tail = blk == nblk - 1;
-      const uint32_t bytes = (uint32_t)(tail ? p.tail_rows : 64) * 128u;
-      const uint32_t dst = sOp0 + o * opb + blk * BLK_BYTES;
-      const uint32_t bar = bars.op(o, blk);
-      mbar_arrive_expect_tx(bar, bytes);
-      if (o < 3) tma_load_2d(dst, tail ? &tmQKVtail : &tmQKV, bar, o * D + h * 64, row0 + blk * 64);
-      else tma_load_2d(dst, tail ? &tmDOtail : &tmDO, bar, h * 64, row0 + blk * 64);
-    };
-    const int first = nblk < 2 ? nblk : 2;
-    load(1, 0);
-    for (int k = 0; k < first; ++k) load(0, k);
-    if (FWD) {
-      for (int k = 1; k < nblk; ++k) load(1, k);
-      for (int k = 0; k < nblk; ++k) load(2, k);
-      for (int k = first; k < nblk; ++k) load(0, k);
-    } else {
-      load(2, 0);
-      for (int k = 0; k < first; ++k) load(3, k);
-      for (int k = 1; k < nblk; ++k) { load(1, k); load(2, k); }
-      for (int k = first; k < nblk; ++k) { load(0, k); load(3, k); }
-    }
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  cg_griddep_wait();
-  if (!FWD) {
-    // per-query constants of phase B (lane = key, column = query): -lse * log2(e) (-inf beyond T => P = 0 there) and delta
-    const float* lb = p.lse + ((long long)n * p.heads + h) * T;
-    const float* db = p.delta + ((long long)n * p.heads + h) * T;
-    for (int i = threadIdx.x; i < 320; i += AT_THREADS) {
-      fscr[i] = i < T ? -lb[i] * LOG2E_F : -INFINITY;
-      fscr[320 + i] = i < T ? db[i] : 0.f;
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars.tmem_slot()) : "memory");
-  TR(warp, 63, 2);
-
-  if (warp < 4) {
-    // ================= four MMA issuer warps.  tcgen05.mma is issued by ONE thread, and with head_dim 64 the instructions are small
-    // (128 x 64 x 16: 32 tensor-pipe cycles), so a single issuing thread is the bottleneck (measured: ~1000 cycles per block).  The
-    // issue work is therefore spread over four warps, each running a lean, warp-converged loop with an elected lane:
-    //   forward   warp 0: S of the even blocks (warpgroup 0)   warp 1: S of the odd blocks      warp 2: O += P V               warp 3: idle
-    //   backward  warp 0: S (S^T) of every block               warp 1: dP (dP^T) of every block  warp 2: dQ | dV      warp 3: (-) | dK
-    // Different issuers never touch the same accumulator; everything else is ordered through the mbarriers.
-    const uint32_t elected = elect_one();
-    uint32_t loaded = 0;  // operand blocks already seen complete (bit o*MAX_BLK + blk)
-    auto need = [&](int o, int blk) {
-      const uint32_t bit = 1u << (o * MAX_BLK + blk);
-      if (!(loaded & bit)) { mbar_wait(bars.op(o, blk), 0); loaded |= bit; }
-    };
-    auto need_tile = [&](int o, int tile) { need(o, 2 * tile); if (2 * tile + 1 < nblk) need(o, 2 * tile + 1); };
-    const int per_tile = FWD ? 2 * nblk : nblk, per_phase = ntiles * nblk;
-    const int G = FWD ? ntiles * per_tile : 2 * per_phase;
-    const uint32_t id_full = idesc_bf16(64, false), id_tail = idesc_bf16(p.tail_rows, false), id_acc = idesc_bf16(64, true);
-    if (warp < 2) {
-      // ---- S-type MMAs: D[128 x ncols] = A_tile[128 x 64] . B_blk[ncols x 64]^T, 4 k-steps of 16
-      const int g0 = FWD ? warp : 0, gstep = FWD ? 2 : 1;
-      for (int g = g0; g < G; g += gstep) {
-        int phase, tile, blk;
-        if (FWD) {
-          tile = g / per_tile;
-          const int r = g - tile * per_tile;
-          phase = r >= nblk ? 1 : 0;
-          blk = r - phase * nblk;
-        } else {
-          phase = g >= per_phase ? 1 : 0;
-          const int r = g - phase * per_phase;
-          tile = r / nblk;
-          blk = r - tile * nblk;
-        }
-        const int b = g % NSB;
-        const bool transposed = !FWD && phase == 1;
-        // forward / backward warp 0: S = Q K^T (S^T = K Q^T);  backward warp 1: dP = dO V^T (dP^T = V dO^T)
-        const int oa = (FWD || warp == 0) ? (transposed ? 1 : 0) : (transposed ? 2 : 3);
-        const int ob = (FWD || warp == 0) ? (transposed ? 0 : 1) : (transposed ? 3 : 2);
-        need_tile(oa, tile);
-        need(ob, blk);
-        mbar_wait(bars.sfree(b), ((uint32_t)(g / NSB) & 1u) ^ 1u);
-        TR(warp, g, 0);
-        tcgen05_fence_after();
-        const uint32_t d_s = tmem_base + s_col<FWD>(b) + ((!FWD && warp == 1) ? 64u : 0u);
-        const uint64_t ad = make_smem_desc(sOp0 + oa * opb + tile * TILE_BYTES), bd = make_smem_desc(sOp0 + ob * opb + blk * BLK_BYTES);
-        const uint32_t idesc = blk == nblk - 1 ? id_tail : id_full;
-        if (elected) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
-          umma_commit(bars.sfull(b));
-        }
-        __syncwarp();
-        TR(warp, g, 1);
-      }
-    } else {
-      // ---- accumulator MMAs of the staged blocks: D[128 x 64] += A_stage[128 x ncols] . B_blk[ncols x 64] (B in MN-major form)
-      // (forward: ONE accumulator issuer.  Splitting the tiles over two issuers would make each of them skip uses of the shared staging
-      // buffers, and an mbarrier parity wait is only sound for a waiter that sees every phase.)
-      const int w = warp - 2;
-      for (int g = (FWD && w != 0) ? G : 0; g < G; ++g) {
-        int phase, tile, blk, sidx, a;
-        uint32_t ause;
-        if (FWD) {
-          tile = g / per_tile;
-          const int r = g - tile * per_tile;
-          phase = r >= nblk ? 1 : 0;
-          if (phase == 0) { g += nblk - 1; continue; }  // pass 0 stages nothing: skip to the tile's pass-1 blocks
-          blk = r - nblk;
-          sidx = tile * nblk + blk;
-          a = tile & 1;
-          ause = (uint32_t)(tile >> 1);
-        } else {
-          phase = g >= per_phase ? 1 : 0;
-          const int r = g - phase * per_phase;
-          tile = r / nblk;
-          blk = r - tile * nblk;
-          sidx = g;
-          a = phase == 1 ? 2 : (tile & 1);
-          ause = (uint32_t)(phase == 1 ? tile : (tile >> 1));
-        }
-        const int pb = sidx % NPB;
-        const bool does_mma = FWD || phase == 1 || w == 0;
-        // B operand: forward V; backward phase A K, phase B dO (warp 2: dV) / Q (warp 3: dK)
-        const int ob = FWD ? 2 : (phase == 0 ? 1 : (w == 0 ? 3 : 0));
-        if (does_mma) need(ob, blk);
-        mbar_wait(bars.pready(pb), (uint32_t)(sidx / NPB) & 1u);
-        TR(warp, g, 0);
-        if (blk == 0) {
-          mbar_wait(bars.accfree(a), (ause & 1u) ^ 1u);
-          if (!FWD && phase == 1 && tile == 0) {
-            // slot 2 (dV | dK) overlays the two dQ slots of phase A: every phase-A tile must have left TMEM first
-            const int u0 = (ntiles + 1) / 2, u1 = ntiles / 2;
-            mbar_wait(bars.accfree(0), (uint32_t)((u0 - 1) & 1));
-            if (u1 > 0) mbar_wait(bars.accfree(1), (uint32_t)((u1 - 1) & 1));
-          }
-        }
-        tcgen05_fence_after();
-        const int ksteps = (blk == nblk - 1 ? p.tail_rows : 64) >> 4;
-        const uint32_t stage = sStage + pb * STAGE_BYTES + ((!FWD && w == 1) ? TILE_BYTES : 0u);  // warp 3: dS^T (second staged tile)
-        const uint32_t d_acc = tmem_base + acc_col<FWD>(a) + ((!FWD && w == 1) ? 64u : 0u);
-        const uint64_t ad = make_smem_desc(stage), bd = make_smem_desc(sOp0 + ob * opb + blk * BLK_BYTES);
-        const bool last = blk == nblk - 1;
-        if (elected) {
-          if (does_mma) {
-            for (int k = 0; k < ksteps; ++k) umma_bf16(d_acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(128 * k), id_acc, (blk | k) != 0 ? 1u : 0u);
-            umma_commit(bars.pfree(pb));
-            if (last) umma_commit(bars.accfull(a));
-          } else {  // backward phase A, warp 3: nothing to multiply, keep the two-arrival barriers in step
-            mbar_arrive(bars.pfree(pb));
-            if (last) mbar_arrive(bars.accfull(a));
-          }
-        }
-        __syncwarp();
-        TR(warp, g, 1);
-      }
-    }
-  } else if (warp >= 4 && warp < 12) {
-    // ================= softmax warpgroups: block g belongs to warpgroup g & 1; thread = one row (TMEM lane) of the tile.
-    // Each warpgroup enumerates ITS blocks directly (g = wg, wg + 2, ...) and decodes (phase, tile, blk) with a few integer ops.
-    const int wg = (warp - 4) >> 2;
-    const int q = warp & 3;
-    const int rl = q * 32 + lane;  // row inside the 128-row tile
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float scale = p.scale, sl2 = p.scale * LOG2E_F;
-    const int tail_cols = T - (nblk - 1) * 64, tail_cols16 = p.tail_rows;
-    float rc0 = 0.f, rc1 = 0.f;     // backward phase A: -lse*log2e and delta of this row; forward: m*c and the running sum
-    float mx = -INFINITY;            // forward pass 0: running maximum of this warpgroup's blocks of the current tile
-    float* smax = fscr;              // [2][128]
-    float* sl = fscr + 256;          // [3][2][128]
-    float* smf = fscr + 1024;        // [3][128]
-    // staging-tile addressing: row rl, 16-byte chunk (4h + j) ^ (rl & 7) = (4h ^ (x & 4)) | (j ^ (x & 3))
-    const uint32_t srow = (uint32_t)rl * 128u, sx = (uint32_t)(rl & 7);
-    const uint32_t shalf0 = srow + (((0u ^ (sx & 4u))) << 4), shalf1 = srow + (((4u ^ (sx & 4u))) << 4);
-    const uint32_t so0 = ((0u ^ (sx & 3u)) << 4), so1 = ((1u ^ (sx & 3u)) << 4), so2 = ((2u ^ (sx & 3u)) << 4), so3 = ((3u ^ (sx & 3u)) << 4);
-    auto stage32 = [&](uint32_t tile_base, int c0, const uint32_t* w) {
-      const uint32_t hb = tile_base + (c0 ? shalf1 : shalf0);
-      st_shared_v4(hb + so0, w[0], w[1], w[2], w[3]);
-      st_shared_v4(hb + so1, w[4], w[5], w[6], w[7]);
-      st_shared_v4(hb + so2, w[8], w[9], w[10], w[11]);
-      st_shared_v4(hb + so3, w[12], w[13], w[14], w[15]);
-    };
-    const int per_tile = FWD ? 2 * nblk : nblk, per_phase = ntiles * nblk;
-    const int G = FWD ? ntiles * per_tile : 2 * per_phase;
-    int synced = 0, finished = 0;  // forward: tiles whose pass-0 maxima have been combined / whose row sums have been published
-    // forward, once per tile and warpgroup (whether or not it owns blocks of that pass): combine the pass-0 maxima of both warpgroups ...
-    auto sync_tile = [&](int t) {
-      smax[wg * 128 + rl] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float m = fmaxf(smax[rl], smax[128 + rl]);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // smax may be overwritten by the next tile only after everybody has read it
-      rc0 = m * sl2;
-      rc1 = 0.f;
-      mx = -INFINITY;
-      if (wg == 0) smf[t * 128 + rl] = m;
-    };
-    // ... and publish this warpgroup's partial row sums of the tile to the epilogue warps
-    auto finish_tile = [&](int t) {
-      sl[(t * 2 + wg) * 128 + rl] = rc1;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars.lready(t));
-    };
-    int cur_tile = -1;
-    for (int g = wg; g < G; g += 2) {
-      int phase, tile, blk, sidx;
-      if (FWD) {
-        tile = g / per_tile;
-        const int r = g - tile * per_tile;
-        phase = r >= nblk ? 1 : 0;
-        blk = r - phase * nblk;
-        sidx = tile * nblk + blk;
-        while (finished < tile) {
-          if (synced <= finished) { sync_tile(finished); ++synced; }
-          finish_tile(finished);
-          ++finished;
-        }
-        if (phase == 1 && synced <= tile) { sync_tile(tile); ++synced; }
-      } else {
-        phase = g >= per_phase ? 1 : 0;
-        const int r = g - phase * per_phase;
-        tile = r / nblk;
-        blk = r - tile * nblk;
-        sidx = g;
-        if (phase == 0 && tile != cur_tile) {
-          const int row = tile * 128 + rl;
-          const bool ok = row < T;
-          rc0 = ok ? -p.lse[((long long)n * p.heads + h) * T + row] * LOG2E_F : 0.f;
-          rc1 = ok ? p.delta[((long long)n * p.heads + h) * T + row] : 0.f;
-          cur_tile = tile;
-        }
-      }
-      const bool wvalid = tile * 128 + q * 32 < T;  // warp-uniform: this warp has at least one real row
-      const bool tail = blk == nblk - 1;
-      const int ncols = tail ? tail_cols : 64, ncols16 = tail ? tail_cols16 : 64;
-      const int b = g % NSB;
-      const uint32_t suse = (uint32_t)(g / NSB);
-      TR(warp, g, 0);
-      mbar_wait(bars.sfull(b), suse & 1u);
-      TR(warp, g, 1);
-      tcgen05_fence_after();
-      const uint32_t t_s = t_lane + s_col<FWD>(b);
-      if (FWD && phase == 0) {
-        if (wvalid) {
-          uint32_t sv[64];
-          tmem_ld32(t_s, sv);
-          if (ncols16 > 32) tmem_ld32(t_s + 32u, sv + 32);
-          tmem_ld_wait();
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bars.sfree(b));
-          if (!tail) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (j < ncols) mx = fmaxf(mx, __uint_as_float(sv[j]));
-          }
-        } else {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bars.sfree(b));
-        }
-        TR(warp, g, 3);
-        continue;
-      }
-      const int pb = sidx % NPB;
-      const uint32_t puse = (uint32_t)(sidx / NPB);
-      const uint32_t stage = sStage + pb * STAGE_BYTES;
-      if (!wvalid) {
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars.sfree(b));
-        // a warp without real rows stages nothing, but it must not run ahead of the barrier phases: its pready arrival for this use
-        // may only happen once the previous use of the staging buffer has been consumed (otherwise early arrivals of LATER blocks
-        // complete the current phase before the warp that does have rows has written its data)
-        mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u);
-      } else if (FWD) {
-        uint32_t sv[64], w[16];
-        tmem_ld32(t_s, sv);
-        if (ncols16 > 32) tmem_ld32(t_s + 32u, sv + 32);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars.sfree(b));  // the S buffer is free for the block after next while the exponentials run
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          if (hlf * 32 < ncols16) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float p0 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j]), sl2, -rc0)), p1 = ex2f(fmaf(__uint_as_float(sv[hlf * 32 + 2 * j + 1]), sl2, -rc0));
-              if (tail) { if (hlf * 32 + 2 * j >= ncols) p0 = 0.f; if (hlf * 32 + 2 * j + 1 >= ncols) p1 = 0.f; }
-              rc1 += p0 + p1;
-              w[j] = pack_bf2(p0, p1);
-            }
-            if (hlf == 0) mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u);  // staging buffer free again
-            stage32(stage, hlf * 32, w);
-          }
-        }
-      } else if (!FWD && T - tile * 128 == 1) {
-        // ---- 1-row tile (T = 128 k + 1): lane 0 owns the only real row; it fetches S and dP from TMEM and hands them to the warp through
-        // shared memory, two columns per lane (a thread-per-row pass would cost the warp a full block of MUFU issue for one lane)
-        uint32_t sv[32], dv[32];
-        float* scr = fscr + 640 + wg * 128;
-        const int ncols = tail ? tail_cols : 64;
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          tmem_ld32(t_s + (uint32_t)(32 * hlf), sv);
-          tmem_ld32(t_s + 64u + (uint32_t)(32 * hlf), dv);
-          tmem_ld_wait();
-          if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              reinterpret_cast<uint4*>(scr + 32 * hlf)[j] = make_uint4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
-              reinterpret_cast<uint4*>(scr + 64 + 32 * hlf)[j] = make_uint4(dv[4 * j], dv[4 * j + 1], dv[4 * j + 2], dv[4 * j + 3]);
-            }
-          }
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars.sfree(b));
-        const bool va = lane < ncols, vb = lane + 32 < ncols;
-        const float s_a = scr[lane], s_b = scr[lane + 32], d_a = scr[64 + lane], d_b = scr[96 + lane];
-        __syncwarp();
-        float p_a, p_b, ds_a, ds_b;
-        if (phase == 0) {  // row = query 128 k: its lse / delta are in rc0 / rc1 of lane 0
-          const float c0 = __shfl_sync(0xffffffffu, rc0, 0), c1 = __shfl_sync(0xffffffffu, rc1, 0);
-          p_a = va ? ex2f(fmaf(s_a, sl2, c0)) : 0.f;
-          p_b = vb ? ex2f(fmaf(s_b, sl2, c0)) : 0.f;
-          ds_a = p_a * scale * (d_a - c1);
-          ds_b = p_b * scale * (d_b - c1);
-        } else {           // row = key 128 k, columns = queries of block blk (-inf in nlse masks the columns beyond T)
-          const float* nl = fscr + blk * 64;
-          p_a = ex2f(fmaf(s_a, sl2, nl[lane]));
-          p_b = ex2f(fmaf(s_b, sl2, nl[lane + 32]));
-          ds_a = p_a * scale * (d_a - nl[320 + lane]);
-          ds_b = p_b * scale * (d_b - nl[320 + lane + 32]);
-        }
-        mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u);  // staging buffer free again
-        // row 0 of the staged tile(s): no swizzle permutation.  Phase A stages dS; phase B stages P^T and dS^T.
-        st_shared_b16(stage + (uint32_t)lane * 2u, phase == 0 ? ds_a : p_a);
-        st_shared_b16(stage + 64u + (uint32_t)lane * 2u, phase == 0 ? ds_b : p_b);
-        if (phase == 1) {
-          st_shared_b16(stage + TILE_BYTES + (uint32_t)lane * 2u, ds_a);
-          st_shared_b16(stage + TILE_BYTES + 64u + (uint32_t)lane * 2u, ds_b);
-        }
-      } else {
-        // backward: S and dP in 16-column pieces, the loads of piece i+1 in flight while piece i is processed
-        uint32_t sv[2][16], dv[2][16], w0[8], w1[8];
-        const int npieces = ncols16 >> 4;
-        tmem_ld16(t_s, sv[0]);
-        tmem_ld16(t_s + 64u, dv[0]);
-        tmem_ld_wait();
-        bool waited = false;
-#pragma unroll
-        for (int pc = 0; pc < 4; ++pc) {
-          if (pc < npieces) {
-            const int cur = pc & 1;
-            if (pc + 1 < npieces) {
-              tmem_ld16(t_s + (uint32_t)(16 * (pc + 1)), sv[cur ^ 1]);
-              tmem_ld16(t_s + 64u + (uint32_t)(16 * (pc + 1)), dv[cur ^ 1]);
-            }
-            if (phase == 0) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float p0 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j]), sl2, rc0)), p1 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j + 1]), sl2, rc0));
-                if (tail) { if (16 * pc + 2 * j >= ncols) p0 = 0.f; if (16 * pc + 2 * j + 1 >= ncols) p1 = 0.f; }
-                w0[j] = pack_bf2(p0 * scale * (__uint_as_float(dv[cur][2 * j]) - rc1), p1 * scale * (__uint_as_float(dv[cur][2 * j + 1]) - rc1));
-              }
-            } else {
-              const float* nl = fscr + blk * 64 + 16 * pc;  // per-query constants: broadcast reads
-              const float* dl = nl + 320;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 l2 = *reinterpret_cast<const float2*>(nl + 2 * j), d2 = *reinterpret_cast<const float2*>(dl + 2 * j);
-                const float p0 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j]), sl2, l2.x)), p1 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j + 1]), sl2, l2.y));
-                w0[j] = pack_bf2(p0, p1);
-                w1[j] = pack_bf2(p0 * scale * (__uint_as_float(dv[cur][2 * j]) - d2.x), p1 * scale * (__uint_as_float(dv[cur][2 * j + 1]) - d2.y));
-              }
-            }
-            if (!waited) { mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u); waited = true; }  // staging buffer free again
-            {
-              const uint32_t hb = stage + ((pc & 2) ? shalf1 : shalf0);
-              st_shared_v4(hb + ((pc & 1) ? so2 : so0), w0[0], w0[1], w0[2], w0[3]);
-              st_shared_v4(hb + ((pc & 1) ? so3 : so1), w0[4], w0[5], w0[6], w0[7]);
-              if (phase == 1) {
-                st_shared_v4(hb + TILE_BYTES + ((pc & 1) ? so2 : so0), w1[0], w1[1], w1[2], w1[3]);
-                st_shared_v4(hb + TILE_BYTES + ((pc & 1) ? so3 : so1), w1[4], w1[5], w1[6], w1[7]);
-              }
-            }
-            if (pc + 1 < npieces) {
-              tmem_ld_wait();
-            } else {  // every TMEM read of this block has completed (the wait of the previous piece covered this one's loads)
-              tcgen05_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bars.sfree(b));
-            }
-          }
-        }
-      }
-      TR(warp, g, 2);
-      fence_proxy_async_smem();  // generic-proxy writes of the staged operand -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars.pready(pb));
-      TR(warp, g, 3);
-    }
-    if (FWD) {
-      while (finished < ntiles) {
-        if (synced <= finished) { sync_tile(finished); ++synced; }
-        finish_tile(finished);
-        ++finished;
-      }
-    }
-  } else if (warp >= 12) {
-    // ================= epilogue: finished accumulator tiles -> HBM
-    const int q = warp & 3;
-    const int rl = q * 32 + lane;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* sl = fscr + 256;
-    float* smf = fscr + 1024;
-    const int total = FWD ? ntiles : 2 * ntiles;
-    for (int tc = 0; tc < total; ++tc) {
-      const int phase = FWD ? 0 : tc / ntiles, tile = FWD ? tc : tc - phase * ntiles;
-      const int a = phase == 1 ? 2 : (tc & 1);
-      const uint32_t par = (uint32_t)((phase == 1 ? tile : (tc >> 1)) & 1);
-      const int row = tile * 128 + rl;
-      mbar_wait(bars.accfull(a), par);
-      if (FWD) mbar_wait(bars.lready(tile), 0);
-      TR(warp, tc, 0);
-      tcgen05_fence_after();
-      if (tile * 128 + q * 32 < T) {
-        uint32_t v0[32], v1[32];
-        const uint32_t col = acc_col<FWD>(a);
-        tmem_ld32(t_lane + col, v0);
-        tmem_ld32(t_lane + col + 32u, v1);
-        tmem_ld_wait();
-        if (FWD) {
-          const float l = sl[(tile * 2 + 0) * 128 + rl] + sl[(tile * 2 + 1) * 128 + rl];
-          const float m = smf[tile * 128 + rl];
-          if (row < T) {
-            store_row64_bf16(p.ctx + ((long long)(row0 + row)) * D + h * 64, v0, v1, 1.f / l);
-            p.lse[((long long)n * p.heads + h) * T + row] = m * p.scale + logf(l);
-          }
-        } else if (phase == 0) {
-          if (row < T) store_row64_bf16(p.dqkv + ((long long)(row0 + row)) * 3 * D + h * 64, v0, v1, 1.f);
-        } else {
-          if (row < T) store_row64_bf16(p.dqkv + ((long long)(row0 + row)) * 3 * D + 2 * D + h * 64, v0, v1, 1.f);  // dV
-          tmem_ld32(t_lane + col + 64u, v0);
-          tmem_ld32(t_lane + col + 96u, v1);
-          tmem_ld_wait();
-          if (row < T) store_row64_bf16(p.dqkv + ((long long)(row0 + row)) * 3 * D + D + h * 64, v0, v1, 1.f);  // dK
-        }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars.accfree(a));
-      TR(warp, tc, 1);
-    }
-  }
-  TR(warp, 63, 3);
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ forward (online softmax, persistent)
 // PERSISTENT kernel: one CTA per SM walks the (image, head) items w = blockIdx.x, blockIdx.x + gridDim.x, ... and the block stream runs
@@ -817,7 +233,7 @@ struct FBars {
   __device__ __forceinline__ uint32_t tmem_slot() const { return base + 440u; }
 };
 constexpr uint32_t FBARS_BYTES = 448 + 16;
-constexpr uint32_t FWD_FLOATS = 4096 + 640;  // sm[4][4][128], sl[4][4][128], edge scratch [640]
+constexpr uint32_t FWD_FLOATS = 4096 + 1024;  // sm[4][4][128], sl[4][4][128], edge scratch [1024]
 constexpr float RESCALE_LOG2 = 8.f;
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
@@ -832,55 +248,154 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// The edge token of the forward (T = Tp + 1, Tp a multiple of 64), on CUDA cores, by the 128 threads of the four epilogue warps; a
-// Both operand rows of a dot product are read from shared memory chunk by chunk (the fixed row as broadcast loads) instead of keeping
-// the fixed row in registers: a spilled register costs an L2 round trip in these kernels (shared memory leaves ~28 KB of L1), and
-// the compiler hoists the unpacking of a register-resident row out of the key loop (64 live floats -> spills).
-//   * the edge QUERY row against all T keys -> ctx_row (64 bf16), lse_out
-//   * the edge KEY against this thread's rows rl and 128 + rl -> returned (log2 units, -inf beyond Tp): the third partial result of the
-//     tile merge;  v_e as floats -> pvec[552 .. 616)
-// scratch pvec: [288] scores / numerators, [8] reductions, [4][32] float2 partial outputs, [64] v_e
-__device__ __forceinline__ float2 fwd_edge_token(uint32_t sQ, uint32_t sK, uint32_t sV, int Tp, float sl2, float* pvec, __nv_bfloat16* ctx_row, float* lse_out) {
-  const int rl = threadIdx.x & 127, q = rl >> 5, lane = rl & 31;
+// ---- warp-level mma.sync helpers of the edge-token path.  The edge token needs matrix-VECTOR products only (a [rows x 64] operand
+// against one 64-long row, and one weight vector against the rows of an operand); on CUDA cores they cost ~3000 instructions per thread
+// and item and slowed the softmax warps sharing the SM sub-partitions.  As m16n8k16 MMAs with the vector in column 0 of B (or row 0 of
+// A) they take a few hundred instructions per warp; operands are read with ldmatrix straight from the TMA-written 128B-swizzled tiles.
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816(float c[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// B fragments of a 64-long bf16 row (row `r` of an operand buffer, r % 8 == 0: not permuted by the swizzle) placed in column 0 of B:
+// vb[2 kk], vb[2 kk + 1] for the four k-steps; zero in the lanes that hold other columns
+__device__ __forceinline__ void load_vec_bfrag(uint32_t buf, int r, uint32_t vb[8]) {
+  const int lane = threadIdx.x & 31, t = lane & 3;
+  const uint32_t rowb = buf + (uint32_t)r * 128u;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    vb[2 * kk] = lane < 4 ? lds32(rowb + (uint32_t)(8 * kk + t) * 4u) : 0u;
+    vb[2 * kk + 1] = lane < 4 ? lds32(rowb + (uint32_t)(8 * kk + t + 4) * 4u) : 0u;
+  }
+}
+// rows [r0, r0 + 16) of a swizzled [rows x 64] bf16 buffer times the vector of vb: lanes with (lane & 3) == 0 return the products of rows
+// r0 + (lane >> 2) (.x) and r0 + (lane >> 2) + 8 (.y)
+__device__ __forceinline__ float2 mv16(uint32_t buf, int r0, const uint32_t vb[8]) {
+  const int lane = threadIdx.x & 31;
+  const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a0, a1, a2, a3;
+    ldsm_x4(buf + swz_off(row, kk * 2 + (lane >> 4)), a0, a1, a2, a3);
+    mma_bf16_16816(c, a0, a1, a2, a3, vb[2 * kk], vb[2 * kk + 1]);
+  }
+  return make_float2(c[0], c[2]);
+}
+// two independent row groups at once (the four chained MMAs of one group leave the pipe mostly idle)
+__device__ __forceinline__ void mv16x2(uint32_t buf, int r0a, int r0b, const uint32_t vb[8], float2& ra, float2& rb) {
+  const int lane = threadIdx.x & 31;
+  const int rowa = r0a + (lane & 7) + ((lane >> 3) & 1) * 8, rowb = r0b + (lane & 7) + ((lane >> 3) & 1) * 8;
+  float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+    ldsm_x4(buf + swz_off(rowa, kk * 2 + (lane >> 4)), a0, a1, a2, a3);
+    ldsm_x4(buf + swz_off(rowb, kk * 2 + (lane >> 4)), b0, b1, b2, b3);
+    mma_bf16_16816(ca, a0, a1, a2, a3, vb[2 * kk], vb[2 * kk + 1]);
+    mma_bf16_16816(cb, b0, b1, b2, b3, vb[2 * kk], vb[2 * kk + 1]);
+  }
+  ra = make_float2(ca[0], ca[2]);
+  rb = make_float2(cb[0], cb[2]);
+}
+// acc[n][.] += vec[k0 .. k0 + 16) (fp32 in shared memory, rounded to bf16 like the staged P / dS of the pipeline) times rows [k0, k0 + 16)
+// of a swizzled [rows x 64] bf16 buffer: the vector sits in row 0 of A; lanes 0-3 hold the result, acc[n][0..1] = columns 8 n + 2 t, + 1
+__device__ __forceinline__ void vm16(uint32_t buf, int k0, const float* vec, float acc[8][4]) {
+  const int lane = threadIdx.x & 31, t = lane & 3;
+  uint32_t a0 = 0u, a2 = 0u;
+  if (lane < 4) {
+    const float2 x = *reinterpret_cast<const float2*>(vec + k0 + 2 * t), y = *reinterpret_cast<const float2*>(vec + k0 + 2 * t + 8);
+    a0 = pack_bf2(x.x, x.y);
+    a2 = pack_bf2(y.x, y.y);
+  }
+  const int row = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  uint32_t b[4][4];
+#pragma unroll
+  for (int cp = 0; cp < 4; ++cp) ldsm_x4_t(buf + swz_off(row, cp * 2 + (lane >> 4)), b[cp][0], b[cp][1], b[cp][2], b[cp][3]);
+#pragma unroll
+  for (int cp = 0; cp < 4; ++cp) {
+    mma_bf16_16816(acc[2 * cp], a0, 0u, a2, 0u, b[cp][0], b[cp][1]);
+    mma_bf16_16816(acc[2 * cp + 1], a0, 0u, a2, 0u, b[cp][2], b[cp][3]);
+  }
+}
+
+// The edge token of the forward (T = Tp + 1, Tp a multiple of 64), by the four epilogue warps (128 threads) with warp-level MMAs:
+//   * the edge QUERY row against all T keys (scores = K q_e, softmax, O_e = p V) -> ctx_row (64 bf16), lse_out
+//   * the edge KEY against every other row (Q k_e) -> returned for this thread's rows rl and 128 + rl (log2 units, -inf beyond Tp): the
+//     third partial result of the tile merge;  v_e as floats -> pvec[552 .. 616)
+// scratch pvec: [288] scores / numerators, [8] reductions, [4][64] partial outputs, [256] edge-key scores; vedge: [64] v_e as floats
+#ifdef CG_ATTN_TRACE
+#define TRE(ev) do { if (tr != nullptr && (threadIdx.x & 31) == 0) tr[ev] = clock64(); } while (0)
+#else
+#define TRE(ev) do { } while (0)
+#endif
+// Two parts: A reads Q and K (scores of the edge query, scores of the edge key), B reads V (softmax of the edge query row, its output
+// row, v_e) -- the caller runs A early, because Q / K are single buffered and their reload waits for it, and B later.
+__device__ __forceinline__ float2 fwd_edge_token_a(uint32_t sQ, uint32_t sK, int Tp, float sl2, float* pvec, long long* tr) {
+  const int rl = threadIdx.x & 127, q = rl >> 5, lane = rl & 31, g = lane >> 2, t = lane & 3;
   const int T = Tp + 1;
+  float* sev = pvec + 552;    // [256]
+  {
+    uint32_t vb[8];
+    load_vec_bfrag(sQ, Tp, vb);  // q_e
+    const int ng = Tp >> 4;  // full key groups; group ng holds the edge key itself in its row 0
+#pragma unroll 1
+    for (int rg = q; rg <= ng; rg += 8) {  // two groups per step (independent MMA chains)
+      const int rg2 = rg + 4 <= ng ? rg + 4 : rg;
+      float2 c, c2;
+      mv16x2(sK, rg * 16, rg2 * 16, vb, c, c2);
+      if (t == 0) {
+        const int j0 = rg * 16 + g, j1 = j0 + 8, k0 = rg2 * 16 + g, k1 = k0 + 8;
+        pvec[j0] = j0 < T ? c.x * sl2 : -INFINITY;
+        pvec[j1] = j1 < T ? c.y * sl2 : -INFINITY;
+        pvec[k0] = k0 < T ? c2.x * sl2 : -INFINITY;
+        pvec[k1] = k1 < T ? c2.y * sl2 : -INFINITY;
+      }
+    }
+    TRE(0);
+    load_vec_bfrag(sK, Tp, vb);  // k_e
+#pragma unroll 1
+    for (int rg = q; rg < ng; rg += 8) {
+      const int rg2 = rg + 4 < ng ? rg + 4 : rg;
+      float2 c, c2;
+      mv16x2(sQ, rg * 16, rg2 * 16, vb, c, c2);
+      if (t == 0) {
+        sev[rg * 16 + g] = c.x * sl2; sev[rg * 16 + g + 8] = c.y * sl2;
+        sev[rg2 * 16 + g] = c2.x * sl2; sev[rg2 * 16 + g + 8] = c2.y * sl2;
+      }
+    }
+  }
+  TRE(1);
+  asm volatile("bar.sync 2, 128;" ::: "memory");
+  return make_float2(rl < Tp ? sev[rl] : -INFINITY, 128 + rl < Tp ? sev[128 + rl] : -INFINITY);
+}
+__device__ __forceinline__ void fwd_edge_token_b(uint32_t sV, int Tp, float* pvec, float* vedge, __nv_bfloat16* ctx_row, float* lse_out, long long* tr) {
+  const int rl = threadIdx.x & 127, q = rl >> 5, lane = rl & 31, t = lane & 3;
   float* red = pvec + 288;
-  float2* part = reinterpret_cast<float2*>(pvec + 296);
-  float* vedge = pvec + 552;
-  float mx;
-  {
-    // corner s_ee: every warp computes it redundantly (rows Tp of Q and K are not permuted by the swizzle: Tp % 8 == 0)
-    const uint32_t wq = lds32(sQ + (uint32_t)Tp * 128u + (uint32_t)lane * 4u), wk = lds32(sK + (uint32_t)Tp * 128u + (uint32_t)lane * 4u);
-    mx = warp_sum(fmaf(bf_lo(wq), bf_lo(wk), bf_hi(wq) * bf_hi(wk))) * sl2;
-    if (rl == 0) pvec[Tp] = mx;
-#pragma unroll 1
-    for (int j = rl; j < Tp; j += 128) {  // rolled on purpose (code size)
-      const float sj = dot_rows2(sK, j, sQ, Tp) * sl2;
-      pvec[j] = sj;
-      mx = fmaxf(mx, sj);
-    }
-  }
-  float2 se = make_float2(-INFINITY, -INFINITY);
-  {
-#pragma unroll 1
-    for (int t = 0; t < 2; ++t) {
-      const int r = t * 128 + rl;
-      const float v = r < Tp ? dot_rows2(sQ, r, sK, Tp) * sl2 : -INFINITY;
-      if (t == 0) se.x = v; else se.y = v;
-    }
-  }
+  float* part = pvec + 296;   // [4][64]
   if (rl < 32) {
     const uint32_t v2 = lds32(sV + (uint32_t)Tp * 128u + (uint32_t)rl * 4u);
     vedge[2 * rl] = bf_lo(v2);
     vedge[2 * rl + 1] = bf_hi(v2);
   }
+  TRE(2);
+  const int ngrp = (Tp >> 4) + 1;  // pvec holds 16 ngrp entries
+  float mx = -INFINITY;
+  for (int j = rl; j < 16 * ngrp; j += 128) mx = fmaxf(mx, pvec[j]);
   mx = warp_max_f(mx);
   if (lane == 0) red[q] = mx;
   asm volatile("bar.sync 2, 128;" ::: "memory");
   mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
   float l = 0.f;
-#pragma unroll 1
-  for (int j = rl; j < T; j += 128) {
-    const float pj = ex2f(pvec[j] - mx);
+  for (int j = rl; j < 16 * ngrp; j += 128) {
+    const float pj = ex2f(pvec[j] - mx);  // 0 beyond T
     pvec[j] = pj;
     l += pj;
   }
@@ -888,31 +403,30 @@ __device__ __forceinline__ float2 fwd_edge_token(uint32_t sQ, uint32_t sK, uint3
   if (lane == 0) red[4 + q] = l;
   asm volatile("bar.sync 2, 128;" ::: "memory");
   l = (red[4] + red[5]) + (red[6] + red[7]);
-  // O_e[d] = sum_j p_j V[j][d]: warp q takes the keys j = q (mod 4); lane owns d = 2 lane, 2 lane + 1 (one 32-bit word of a V row)
-  const uint32_t vcol = ((uint32_t)(lane >> 2) << 4), vin = (uint32_t)(lane & 3) << 2;
-  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-  int j = q;
-#pragma unroll 4
-  for (; j + 4 < T; j += 8) {
-    const uint32_t va = lds32(sV + (uint32_t)j * 128u + (vcol ^ ((uint32_t)(j & 7) << 4)) + vin);
-    const uint32_t vb = lds32(sV + (uint32_t)(j + 4) * 128u + (vcol ^ ((uint32_t)((j + 4) & 7) << 4)) + vin);
-    const float pa = pvec[j], pb = pvec[j + 4];
-    o0 = fmaf(pa, bf_lo(va), o0); o1 = fmaf(pa, bf_hi(va), o1);
-    o2 = fmaf(pb, bf_lo(vb), o2); o3 = fmaf(pb, bf_hi(vb), o3);
+  TRE(3);
+  {
+    // O_e = sum_j p_j V[j]: warp q takes the key groups ks = q (mod 4)
+    float acc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+#pragma unroll 1
+    for (int ks = q; ks < ngrp; ks += 4) vm16(sV, ks * 16, pvec, acc);
+    if (lane < 4) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) *reinterpret_cast<float2*>(part + q * 64 + 8 * n + 2 * t) = make_float2(acc[n][0], acc[n][1]);
+    }
   }
-  if (j < T) {
-    const uint32_t va = lds32(sV + (uint32_t)j * 128u + (vcol ^ ((uint32_t)(j & 7) << 4)) + vin);
-    o0 = fmaf(pvec[j], bf_lo(va), o0); o1 = fmaf(pvec[j], bf_hi(va), o1);
-  }
-  part[q * 32 + lane] = make_float2(o0 + o2, o1 + o3);
+  TRE(4);
   asm volatile("bar.sync 2, 128;" ::: "memory");
+  TRE(5);
   if (q == 0) {
-    const float2 a0 = part[lane], a1 = part[32 + lane], a2 = part[64 + lane], a3 = part[96 + lane];
     const float inv = __fdividef(1.f, l);
+    const float2 a0 = *reinterpret_cast<const float2*>(part + 2 * lane), a1 = *reinterpret_cast<const float2*>(part + 64 + 2 * lane);
+    const float2 a2 = *reinterpret_cast<const float2*>(part + 128 + 2 * lane), a3 = *reinterpret_cast<const float2*>(part + 192 + 2 * lane);
     reinterpret_cast<uint32_t*>(ctx_row)[lane] = pack_bf2(((a0.x + a1.x) + (a2.x + a3.x)) * inv, ((a0.y + a1.y) + (a2.y + a3.y)) * inv);
     if (lane == 0) *lse_out = mx * (1.f / LOG2E_F) + logf(l);
   }
-  return se;
+  asm volatile("bar.sync 2, 128;" ::: "memory");  // vedge is complete for every epilogue warp; pvec / part may be reused
 }
 
 // time-line probe of the persistent kernel: CTA 0, its third item (warm caches, steady state)
@@ -922,8 +436,15 @@ __device__ __forceinline__ float2 fwd_edge_token(uint32_t sQ, uint32_t sK, uint3
     if (p.trace != nullptr && blockIdx.x == 0 && it == 2 && (threadIdx.x & 31) == 0)                         \
       p.trace[(((slot) * 64 + (idx)) << 3) + (ev)] = clock64();                                              \
   } while (0)
+// every item of CTA 0: idx = 32 + item iteration (< 24)
+#define TRI(slot, ev)                                                                                        \
+  do {                                                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0 && it < 24 && (threadIdx.x & 31) == 0)                         \
+      p.trace[(((slot) * 64 + 32 + it) << 3) + (ev)] = clock64();                                            \
+  } while (0)
 #else
 #define TRF(slot, idx, ev) do { } while (0)
+#define TRI(slot, ev) do { } while (0)
 #endif
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -994,6 +515,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         for (int k = 0; k < nblk_ld; ++k) {
           load(sK, bars.opk(k), kc, k);
           load(sQ, bars.opq(k), qc, k);
+        }
+        // the operands are single (V: double) buffered, so the next item's loads cannot be issued early: pull its tiles into L2 now
+        if (w + (int)gridDim.x < nitems) {
+          const int w2 = w + gridDim.x, n2 = w2 / heads, h2 = w2 - n2 * heads;
+#pragma unroll 1
+          for (int k = 0; k < nblk_ld; ++k) {
+            const CUtensorMap* tm = k == nblk_ld - 1 ? &tmQKVtail : &tmQKV;
+            tma_prefetch_2d(tm, D + h2 * 64, n2 * T + k * 64);
+            tma_prefetch_2d(tm, h2 * 64, n2 * T + k * 64);
+            tma_prefetch_2d(tm, 2 * D + h2 * 64, n2 * T + k * 64);
+          }
         }
       }
     }
@@ -1238,25 +770,54 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     const int rl = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = p.scale * LOG2E_F;
-    const float* vedge = pvec + 552;                          // [64] v_e as floats (written by fwd_edge_token)
+    float* vedge2 = pvec + 808;                               // [2][64] v_e as floats (written by fwd_edge_token), by item parity
     uint32_t euse = 0;  // 4 bits per accumulator slot: its use count (mod 16)
+    // The edge token of item i + 1 is processed BETWEEN the first and the remaining tiles of item i (its Q / K arrive once the S MMAs of
+    // item i are done, V is double buffered): the edge work then never sits between the end of one item and the reload of Q / K for the
+    // next.  (Measured alternatives: at the start of the item's own iteration -> the Q / K reload waits for it, +10% cycles; V part
+    // after the last tile -> no gain.)  This role stays the forward's critical resource at T = 257: ~2 x 2100 cycles of tile merges +
+    // ~9000 of edge work per item against ~12 000 of softmax per warpgroup.  se0 / se1: edge-key scores of this thread's rows in tile 0 / 1.
+    auto edge_a = [&](int wi, int eit, float& s0, float& s1) {  // Q / K part of the edge token of item wi (iteration eit)
+      const uint32_t opar = (uint32_t)eit & 1u;
+      if (edge) {
+        for (int b = 0; b < nblk_ld; ++b) { mbar_wait(bars.opk(b), opar); mbar_wait(bars.opq(b), opar); }
+#ifdef CG_ATTN_TRACE
+        long long* etr = (p.trace != nullptr && blockIdx.x == 0 && eit == 3) ? p.trace + ((warp * 64 + 60) << 3) : nullptr;
+#else
+        long long* etr = nullptr;
+#endif
+        const float2 se = fwd_edge_token_a(sQ, sK, Tp, sl2, pvec, etr);
+        s0 = se.x;
+        s1 = se.y;
+      } else if (eit > 0) {
+        mbar_wait(bars.qkfree(), (uint32_t)(eit - 1) & 1u);  // the arrival below must not land in the previous item's phase
+      }
+      // this role no longer reads Q and K of that item from shared memory (the arrival orders the reads above before the refill)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars.qkfree());
+    };
+    auto edge_b = [&](int wi, int eit) {  // V part
+      const int n = wi / heads, h = wi - n * heads, row0 = n * T, vb = eit & 1;
+      if (edge) {
+        for (int b = 0; b < nblk_ld; ++b) mbar_wait(bars.opv(vb, b), (uint32_t)(eit >> 1) & 1u);
+#ifdef CG_ATTN_TRACE
+        long long* etr = (p.trace != nullptr && blockIdx.x == 0 && eit == 3) ? p.trace + ((warp * 64 + 60) << 3) : nullptr;
+#else
+        long long* etr = nullptr;
+#endif
+        fwd_edge_token_b(sV0 + vb * opb, Tp, pvec, vedge2 + vb * 64, p.ctx + ((long long)(row0 + Tp)) * D + h * 64, p.lse + ((long long)n * heads + h) * T + Tp, etr);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars.vfree(vb));
+    };
+    float se0 = -INFINITY, se1 = -INFINITY, nse0 = -INFINITY, nse1 = -INFINITY;
+    if ((int)blockIdx.x < nitems) { edge_a(blockIdx.x, 0, se0, se1); edge_b(blockIdx.x, 0); }
     int it = 0, gg0 = 0;
     for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it, gg0 += G) {
-      const int n = w / heads, h = w - n * heads, row0 = n * T, vb = it & 1;
-      const uint32_t opar = (uint32_t)it & 1u, vpar = (uint32_t)(it >> 1) & 1u, sVb = sV0 + vb * opb;
-      float se0 = -INFINITY, se1 = -INFINITY;  // edge key scores of this thread's row in tile 0 / 1 (log2 units)
+      const int n = w / heads, h = w - n * heads, row0 = n * T;
+      const float* vedge = vedge2 + (it & 1) * 64;
       TRF(warp, 62, 0);
-      if (edge) {
-        for (int b = 0; b < nblk_ld; ++b) { mbar_wait(bars.opk(b), opar); mbar_wait(bars.opv(vb, b), vpar); mbar_wait(bars.opq(b), opar); }
-        TRF(warp, 61, 0);
-        const float2 se = fwd_edge_token(sQ, sK, sVb, Tp, sl2, pvec, p.ctx + ((long long)(row0 + Tp)) * D + h * 64, p.lse + ((long long)n * heads + h) * T + Tp);
-        se0 = se.x;
-        se1 = se.y;
-        TRF(warp, 61, 1);
-      }
-      // this role no longer reads Q, K, V of the item from shared memory (the barrier arrival orders the reads above before the refill)
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(bars.qkfree()); mbar_arrive(bars.vfree(vb)); }
+      TRI(warp, 0);
       for (int tile = 0; tile < ntiles; ++tile) {
         const int tp = tile & 1, a0 = tp, a1 = 2 + tp;
         // with a single block per tile only warpgroup (running block index) & 1 takes part
@@ -1308,8 +869,521 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         if (has0) euse = (euse & ~(15u << (4 * a0))) | (((u0 + 1u) & 15u) << (4 * a0));
         if (has1) euse = (euse & ~(15u << (4 * a1))) | (((u1 + 1u) & 15u) << (4 * a1));
         TRF(warp, tile, 1);
+        if (tile == 0 && w + (int)gridDim.x < nitems) {
+          TRF(warp, 61, 0);
+          edge_a(w + gridDim.x, it + 1, nse0, nse1);
+          edge_b(w + gridDim.x, it + 1);
+          TRF(warp, 61, 1);
+        }
       }
+      se0 = nse0;
+      se1 = nse1;
       TRF(warp, 62, 1);
+      TRI(warp, 1);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward (persistent)
+// Same organisation as the forward: one CTA per SM walks the (image, head) items; the block stream, the TMEM / staging buffers and all
+// mbarrier phases run across items, so the epilogue of an item's last tile, the edge-token work and the TMEM hand-over overlap the
+// next item.  The four operands (Q, K, V, dO: 4 x 34 KB for T = 257) are single buffered -- all of them are read until the item's last
+// MMAs -- so the next item's loads start when those have completed (one TMA round trip per item instead of a CTA launch, barrier and
+// TMEM set-up, constant loads and a serial epilogue: 13 000 of 61 000 cycles per item before).
+//
+//   phase A (lane = query):  S = Q K^T, dP = dO V^T, dS = P (dP - delta) scale, dQ += dS K
+//   phase B (lane = key):    S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
+//   P is recomputed from the saved log-sum-exp; two orientations instead of a transposed smem operand, no atomics, deterministic.
+//
+//   warp 0   S (S^T) MMAs            warp 1   dP (dP^T) MMAs         warp 2   dQ | dV MMAs       warp 3   dK MMAs + TMA producer
+//   warps 4-11   two softmax warpgroups (block gg -> warpgroup gg & 1, staging buffer gg & 1)      warps 12-15   epilogue + edge token
+//   TMEM: S | dP buffers 3 x (64 + 64) columns [0, 384); dQ slots 0 / 1 at 384 + 64 (tile & 1); phase B: dV at 384, dK at 448 (slot 2,
+//   overlaying the dQ slots: the issuers wait until the epilogue has drained them).
+//
+// Edge token (T = 64 m + 1, e = T - 1): the pipeline covers the first Tp = T - 1 queries and keys.  The epilogue warps compute on CUDA
+// cores  column e:  p_ie, dS_ie (all queries i)   and   row e:  p_ej, dS_ej (all keys j)   from four 64-long dot products per index,
+// then  dQ_e = sum_j dS_ej K_j,  dK_e = sum_i dS_ie Q_i,  dV_e = sum_i p_ie dO_i  and, when they write a tile,
+//   dQ_i += dS_ie K_e        dK_j += dS_ej Q_e        dV_j += p_ej dO_e.
+struct BBars {
+  uint32_t base;
+  __device__ __forceinline__ uint32_t sfull(int b) const { return base + 8u * b; }                // S and dP block in TMEM buffer b     (2 x tcgen05.commit)
+  __device__ __forceinline__ uint32_t sfree(int b) const { return base + 24u + 8u * b; }          // its warpgroup has read it           (4 warps)
+  __device__ __forceinline__ uint32_t pready(int pb) const { return base + 48u + 8u * pb; }       // staging buffer pb is written        (4 warps)
+  __device__ __forceinline__ uint32_t pfree(int pb) const { return base + 64u + 8u * pb; }        // accumulator MMAs have consumed it   (2 issuers)
+  __device__ __forceinline__ uint32_t accfull(int a) const { return base + 80u + 8u * a; }        // accumulator slot a is complete      (2 issuers)
+  __device__ __forceinline__ uint32_t accfree(int a) const { return base + 104u + 8u * a; }       // epilogue has read it                (4 warps)
+  __device__ __forceinline__ uint32_t op(int o, int blk) const { return base + 128u + 8u * (o * MAX_BLK + blk); }  // operand o (Q, K, V, dO), 64-row block (TMA)
+  __device__ __forceinline__ uint32_t opfree() const { return base + 288u; }                      // the item's operands are no longer read (4 issuers + 4 epilogue warps)
+  __device__ __forceinline__ uint32_t cready(int par) const { return base + 296u + 8u * par; }    // per-token constants of an item are in smem (4 warps)
+  __device__ __forceinline__ uint32_t tmem_slot() const { return base + 312u; }
+};
+constexpr uint32_t BBARS_BYTES = 320 + 16;
+// float scratch: constants [2][640] (-lse log2e [320], delta [320]); edge vectors [4][288] (p_ie, dS_ie, p_ej, dS_ej); K_e, Q_e, dO_e as
+// floats [3][64]; partial sums [3][4][32] float2
+constexpr uint32_t BWD_FLOATS = 1280 + 1152 + 192 + 768;
+
+#ifdef CG_ATTN_TRACE
+#define TRB(slot, idx, ev) TRF(slot, idx, ev)
+#else
+#define TRB(slot, idx, ev) do { } while (0)
+#endif
+
+// 64 fp32 accumulator values of one row + coef * vec[0..64) -> 64 bf16 = 128 contiguous bytes (vec: broadcast reads from shared memory)
+__device__ __forceinline__ void store_row64_bf16_axpy(__nv_bfloat16* dst, const uint32_t* a, const uint32_t* b, float coef, const float* vec) {
+  uint32_t w[32];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 v0 = *reinterpret_cast<const float2*>(vec + 2 * j), v1 = *reinterpret_cast<const float2*>(vec + 32 + 2 * j);
+    w[j] = pack_bf2(fmaf(coef, v0.x, __uint_as_float(a[2 * j])), fmaf(coef, v0.y, __uint_as_float(a[2 * j + 1])));
+    w[16 + j] = pack_bf2(fmaf(coef, v1.x, __uint_as_float(b[2 * j])), fmaf(coef, v1.y, __uint_as_float(b[2 * j + 1])));
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st256g(dst + 16 * j, w + 8 * j);
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+    attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKVtail, const __grid_constant__ CUtensorMap tmDO,
+                       const __grid_constant__ CUtensorMap tmDOtail, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  cg_griddep_launch();
+  constexpr int NSB = 3;
+  constexpr uint32_t STAGE_BYTES = 2 * TILE_BYTES;  // phase B stages P^T and dS^T
+  const int T = p.T, heads = p.heads, D = heads * 64;
+  const int edge = p.edge, Tp = T - edge;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = p.ntiles, nblk = p.nblk, nblk_ld = p.nblk_ld;
+  const int per_phase = ntiles * nblk, G = 2 * per_phase, nitems = p.nitems;
+  const uint32_t opb = (uint32_t)((nblk_ld - 1) * 64 + p.ld_tail) * 128u;  // bytes per operand buffer (multiple of 2048)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sOp0 = base;                                   // operands 0 = Q, 1 = K, 2 = V, 3 = dO
+  const uint32_t sStage = base + 4 * opb;                       // 2 x 32 KB; also absorbs the A-operand over-read of the last tile
+  const uint32_t sF = sStage + 2 * STAGE_BYTES;
+  float* fscr = reinterpret_cast<float*>(smem_raw + (sF - smem_u32(smem_raw)));
+  float* csts = fscr;          // [2][640]
+  float* ev = fscr + 1280;     // [4][288]
+  float* evec = fscr + 2432;   // [3][64]: K_e, Q_e, dO_e
+  float* epart = fscr + 2624;  // [3][4][32] float2
+  BBars bars{sF + BWD_FLOATS * 4};
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKVtail) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDOtail) : "memory");
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(bars.sfull(b), 2); mbar_init(bars.sfree(b), 4);
+      mbar_init(bars.accfull(b), 2); mbar_init(bars.accfree(b), 4);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(bars.pready(b), 4); mbar_init(bars.pfree(b), 2); mbar_init(bars.cready(b), 4); }
+    for (int o = 0; o < 4; ++o)
+      for (int k = 0; k < MAX_BLK; ++k) mbar_init(bars.op(o, k), 1);
+    mbar_init(bars.opfree(), 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  cg_griddep_wait();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(bars.tmem_slot()) : "memory");
+
+  if (warp < 4) {
+    // ================= four MMA issuer warps (warp-converged loops, elected lane); warp 3 is also the TMA producer
+    const uint32_t elected = elect_one();
+    const uint32_t id_full = idesc_bf16(64, false), id_tail = idesc_bf16(p.tail_rows, false), id_acc = idesc_bf16(64, true);
+    uint32_t cuse = 0;  // accumulator issuers: bit a = parity of the number of uses of slot a issued so far
+    int it = 0, gg0 = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it, gg0 += G) {
+      const uint32_t opar = (uint32_t)it & 1u;
+      uint32_t loaded = 0;  // operand blocks already seen complete (bit o * MAX_BLK + blk)
+      auto need = [&](int o, int blk) {
+        const uint32_t bit = 1u << (o * MAX_BLK + blk);
+        if (!(loaded & bit)) { mbar_wait(bars.op(o, blk), opar); loaded |= bit; }
+      };
+      if (warp == 3) {
+        if (elected) {
+          // ---- TMA producer: every operand block of the item once, in the order phase A needs them
+          if (it > 0) mbar_wait(bars.opfree(), (uint32_t)(it - 1) & 1u);  // nobody reads the previous item's operands any more
+          const int n = w / heads, h = w - n * heads, row0 = n * T;
+          auto load = [&](int o, int blk) {
+            const bool tail = blk == nblk_ld - 1;
+            const uint32_t bar = bars.op(o, blk);
+            mbar_arrive_expect_tx(bar, (uint32_t)(tail ? p.ld_tail : 64) * 128u);
+            if (o < 3) tma_load_2d(sOp0 + o * opb + blk * BLK_BYTES, tail ? &tmQKVtail : &tmQKV, bar, o * D + h * 64, row0 + blk * 64);
+            else tma_load_2d(sOp0 + o * opb + blk * BLK_BYTES, tail ? &tmDOtail : &tmDO, bar, h * 64, row0 + blk * 64);
+          };
+          const int first = nblk_ld < 2 ? nblk_ld : 2;
+          load(1, 0);
+#pragma unroll 1
+          for (int k = 0; k < first; ++k) load(0, k);
+          load(2, 0);
+#pragma unroll 1
+          for (int k = 0; k < first; ++k) load(3, k);
+#pragma unroll 1
+          for (int k = 1; k < nblk_ld; ++k) { load(1, k); load(2, k); }
+#pragma unroll 1
+          for (int k = first; k < nblk_ld; ++k) { load(0, k); load(3, k); }
+          // single-buffered operands: the next item's loads cannot be issued before this item is finished -- pull its tiles into L2 now
+          if (w + (int)gridDim.x < nitems) {
+            const int w2 = w + gridDim.x, n2 = w2 / heads, h2 = w2 - n2 * heads;
+#pragma unroll 1
+            for (int k = 0; k < nblk_ld; ++k) {
+              const bool tail = k == nblk_ld - 1;
+#pragma unroll 1
+              for (int o = 0; o < 3; ++o) tma_prefetch_2d(tail ? &tmQKVtail : &tmQKV, o * D + h2 * 64, n2 * T + k * 64);
+              tma_prefetch_2d(tail ? &tmDOtail : &tmDO, h2 * 64, n2 * T + k * 64);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      int phase = 0, tile = 0, blk = 0;
+      if (warp < 2) {
+        // ---- S-type MMAs: D[128 x ncols] = A_tile[128 x 64] . B_blk[ncols x 64]^T, 4 k-steps of 16.  warp 0: S = Q K^T (S^T = K Q^T);
+        // warp 1: dP = dO V^T (dP^T = V dO^T)
+        for (int g = 0; g < G; ++g) {
+          const int gg = gg0 + g, b = gg % NSB;
+          const bool transposed = phase == 1;
+          const int oa = warp == 0 ? (transposed ? 1 : 0) : (transposed ? 2 : 3);
+          const int ob = warp == 0 ? (transposed ? 0 : 1) : (transposed ? 3 : 2);
+          need(oa, 2 * tile);
+          if (2 * tile + 1 < nblk) need(oa, 2 * tile + 1);
+          need(ob, blk);
+          mbar_wait(bars.sfree(b), ((uint32_t)(gg / NSB) & 1u) ^ 1u);
+          TRB(warp, g, 0);
+          tcgen05_fence_after();
+          const uint32_t d_s = tmem_base + (uint32_t)(b * 128) + (warp == 1 ? 64u : 0u);
+          const uint64_t ad = make_smem_desc(sOp0 + oa * opb + tile * TILE_BYTES), bd = make_smem_desc(sOp0 + ob * opb + blk * BLK_BYTES);
+          const uint32_t idesc = blk == nblk - 1 ? id_tail : id_full;
+          if (elected) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+            umma_commit(bars.sfull(b));
+          }
+          __syncwarp();
+          TRB(warp, g, 1);
+          if (++blk == nblk) { blk = 0; if (++tile == ntiles) { tile = 0; ++phase; } }
+        }
+      } else {
+        // ---- accumulator MMAs of the staged blocks: D[128 x 64] += A_stage[128 x ncols] . B_blk[ncols x 64] (B in MN-major form)
+        // warp 2: dQ += dS K (phase A), dV += P^T dO (phase B); warp 3: dK += dS^T Q (phase B), plain arrivals in phase A
+        const int wi = warp - 2;
+        for (int g = 0; g < G; ++g) {
+          const int gg = gg0 + g, pb = gg & 1;
+          const int a = phase == 1 ? 2 : (tile & 1);
+          const bool does_mma = phase == 1 || wi == 0;
+          const int ob = phase == 0 ? 1 : (wi == 0 ? 3 : 0);
+          if (does_mma) need(ob, blk);
+          mbar_wait(bars.pready(pb), (uint32_t)(gg >> 1) & 1u);
+          TRB(warp, g, 0);
+          if (blk == 0) {
+            // the slot's previous use must have been read by the epilogue.  Slot 2 (dV | dK) overlays the two dQ slots: phase B waits for
+            // the latest use of both of them, phase A for the latest use of slot 2 (the previous item's last tile).
+            if (phase == 1) {
+              mbar_wait(bars.accfree(2), ((cuse >> 2) & 1u) ^ 1u);
+              if (tile == 0) { mbar_wait(bars.accfree(0), (cuse & 1u) ^ 1u); mbar_wait(bars.accfree(1), ((cuse >> 1) & 1u) ^ 1u); }
+            } else {
+              mbar_wait(bars.accfree(a), ((cuse >> a) & 1u) ^ 1u);
+              mbar_wait(bars.accfree(2), ((cuse >> 2) & 1u) ^ 1u);
+            }
+          }
+          tcgen05_fence_after();
+          const int ksteps = (blk == nblk - 1 ? p.tail_rows : 64) >> 4;
+          const uint32_t stage = sStage + pb * STAGE_BYTES + (wi == 1 ? TILE_BYTES : 0u);  // warp 3: dS^T (second staged tile)
+          const uint32_t d_acc = tmem_base + (a == 2 ? 384u : 384u + 64u * a) + (wi == 1 ? 64u : 0u);
+          const uint64_t ad = make_smem_desc(stage), bd = make_smem_desc(sOp0 + ob * opb + blk * BLK_BYTES);
+          const bool last = blk == nblk - 1;
+          if (elected) {
+            if (does_mma) {
+              for (int k = 0; k < ksteps; ++k) umma_bf16(d_acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(128 * k), id_acc, (blk | k) != 0 ? 1u : 0u);
+              umma_commit(bars.pfree(pb));
+              if (last) umma_commit(bars.accfull(a));
+            } else {  // phase A, warp 3: nothing to multiply, keep the two-arrival barriers in step
+              mbar_arrive(bars.pfree(pb));
+              if (last) mbar_arrive(bars.accfull(a));
+            }
+          }
+          __syncwarp();
+          TRB(warp, g, 1);
+          if (last) cuse ^= 1u << a;
+          if (++blk == nblk) { blk = 0; if (++tile == ntiles) { tile = 0; ++phase; } }
+        }
+      }
+      // observe every phase of every operand barrier (a parity wait is only sound then), then release the operands: the arrival fires
+      // when all MMAs this warp has issued so far have completed
+#pragma unroll 1
+      for (int o = 0; o < 4; ++o)
+#pragma unroll 1
+        for (int k = 0; k < nblk_ld; ++k) need(o, k);
+      if (elected) umma_commit(bars.opfree());
+      __syncwarp();
+    }
+  } else if (warp < 12) {
+    // ================= softmax warpgroups: block gg belongs to warpgroup gg & 1 (G is even: g & 1); thread = one row (TMEM lane) of the tile
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int rl = q * 32 + lane;  // row inside the 128-row tile
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float scale = p.scale, sl2 = p.scale * LOG2E_F;
+    const int tail_cols = Tp - (nblk - 1) * 64, tail_cols16 = p.tail_rows;
+    const uint32_t sx = (uint32_t)(rl & 7) << 4;  // 128B swizzle of this thread's row of a staged tile: 16-byte chunk c sits at (c << 4) ^ sx
+    int it = 0, gg0 = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it, gg0 += G) {
+      mbar_wait(bars.cready(it & 1), (uint32_t)(it >> 1) & 1u);
+      const float* cst = csts + (it & 1) * 640;  // [0, 320): -lse log2e (-inf beyond T), [320, 640): delta
+      float rc0 = 0.f, rc1 = 0.f;  // phase A: -lse * log2e and delta of this thread's query row
+      int phase = 0, tile = 0, blk = wg, cur_tile = -1;
+      while (blk >= nblk) { blk -= nblk; if (++tile == ntiles) { tile = 0; ++phase; } }
+      for (int g = wg; g < G; g += 2) {
+        const int gg = gg0 + g;
+        if (phase == 0 && tile != cur_tile) {
+          const int row = tile * 128 + rl;
+          rc0 = row < Tp ? cst[row] : 0.f;
+          rc1 = row < Tp ? cst[320 + row] : 0.f;
+          cur_tile = tile;
+        }
+        const bool wvalid = tile * 128 + q * 32 < Tp;  // warp-uniform: this warp has at least one real row
+        const bool tail = blk == nblk - 1;
+        const int ncols = tail ? tail_cols : 64, ncols16 = tail ? tail_cols16 : 64;
+        const int b = gg % NSB, pb = gg & 1;
+        const uint32_t suse = (uint32_t)(gg / NSB), puse = (uint32_t)(gg >> 1);
+        TRB(warp, g, 0);
+        mbar_wait(bars.sfull(b), suse & 1u);
+        TRB(warp, g, 1);
+        tcgen05_fence_after();
+        const uint32_t t_s = t_lane + (uint32_t)(b * 128);
+        const uint32_t stage = sStage + pb * STAGE_BYTES + (uint32_t)rl * 128u;
+        if (!wvalid) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars.sfree(b));
+          // a warp without real rows stages nothing, but it must not run ahead of the barrier phases: its pready arrival for this use
+          // may only happen once the previous use of the staging buffer has been consumed (otherwise early arrivals of LATER blocks
+          // complete the current phase before the warp that does have rows has written its data)
+          mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u);
+        } else {
+          // S and dP in 16-column pieces, the loads of piece i+1 in flight while piece i is processed
+          uint32_t sv[2][16], dv[2][16], w0[8], w1[8];
+          const int npieces = ncols16 >> 4;
+          tmem_ld16(t_s, sv[0]);
+          tmem_ld16(t_s + 64u, dv[0]);
+          tmem_ld_wait();
+          bool waited = false;
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            if (pc < npieces) {
+              const int cur = pc & 1;
+              if (pc + 1 < npieces) {
+                tmem_ld16(t_s + (uint32_t)(16 * (pc + 1)), sv[cur ^ 1]);
+                tmem_ld16(t_s + 64u + (uint32_t)(16 * (pc + 1)), dv[cur ^ 1]);
+              }
+              if (phase == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float p0 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j]), sl2, rc0)), p1 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j + 1]), sl2, rc0));
+                  if (tail) { if (16 * pc + 2 * j >= ncols) p0 = 0.f; if (16 * pc + 2 * j + 1 >= ncols) p1 = 0.f; }
+                  w0[j] = pack_bf2(p0 * scale * (__uint_as_float(dv[cur][2 * j]) - rc1), p1 * scale * (__uint_as_float(dv[cur][2 * j + 1]) - rc1));
+                }
+              } else {
+                const float* nl = cst + blk * 64 + 16 * pc;  // per-query constants: broadcast reads
+                const float* dl = nl + 320;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 l2 = *reinterpret_cast<const float2*>(nl + 2 * j), d2 = *reinterpret_cast<const float2*>(dl + 2 * j);
+                  float p0 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j]), sl2, l2.x)), p1 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j + 1]), sl2, l2.y));
+                  if (tail) { if (16 * pc + 2 * j >= ncols) p0 = 0.f; if (16 * pc + 2 * j + 1 >= ncols) p1 = 0.f; }
+                  w0[j] = pack_bf2(p0, p1);
+                  w1[j] = pack_bf2(p0 * scale * (__uint_as_float(dv[cur][2 * j]) - d2.x), p1 * scale * (__uint_as_float(dv[cur][2 * j + 1]) - d2.y));
+                }
+              }
+              if (!waited) { mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u); waited = true; }  // staging buffer free again
+              {
+                const uint32_t c0 = ((uint32_t)(pc * 32)) ^ sx, c1 = ((uint32_t)(pc * 32 + 16)) ^ sx;
+                st_shared_v4(stage + c0, w0[0], w0[1], w0[2], w0[3]);
+                st_shared_v4(stage + c1, w0[4], w0[5], w0[6], w0[7]);
+                if (phase == 1) {
+                  st_shared_v4(stage + TILE_BYTES + c0, w1[0], w1[1], w1[2], w1[3]);
+                  st_shared_v4(stage + TILE_BYTES + c1, w1[4], w1[5], w1[6], w1[7]);
+                }
+              }
+              if (pc + 1 < npieces) {
+                tmem_ld_wait();
+              } else {  // every TMEM read of this block has completed (the wait of the previous piece covered this one's loads)
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars.sfree(b));
+              }
+            }
+          }
+        }
+        TRB(warp, g, 2);
+        fence_proxy_async_smem();  // generic-proxy writes of the staged operand -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.pready(pb));
+        TRB(warp, g, 3);
+        blk += 2;
+        while (blk >= nblk) { blk -= nblk; if (++tile == ntiles) { tile = 0; ++phase; } }
+      }
+    }
+  } else {
+    // ================= epilogue warps: per-token constants, edge token, finished accumulator tiles -> HBM
+    const int q = warp & 3;
+    const int rl = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float scale = p.scale, sl2 = p.scale * LOG2E_F;
+    uint32_t euse = 0;  // bit a: parity of the use count of accumulator slot a
+    auto load_consts = [&](int item, int par) {
+      const int n = item / heads, h = item - n * heads;
+      const float* lb = p.lse + ((long long)n * heads + h) * T;
+      const float* db = p.delta + ((long long)n * heads + h) * T;
+      float* c = csts + par * 640;
+      for (int i = rl; i < 320; i += 128) {
+        c[i] = i < T ? -lb[i] * LOG2E_F : -INFINITY;
+        c[320 + i] = i < T ? db[i] : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars.cready(par));
+    };
+    if ((int)blockIdx.x < nitems) load_consts(blockIdx.x, 0);
+    int it = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
+      const int n = w / heads, h = w - n * heads, row0 = n * T;
+      const uint32_t opar = (uint32_t)it & 1u;
+      // constants of the NEXT item (its buffer was last read by item it - 1, whose tiles this role has already finished)
+      if (w + (int)gridDim.x < nitems) load_consts(w + gridDim.x, (it + 1) & 1);
+      const float* cst = csts + (it & 1) * 640;
+      __nv_bfloat16* out = p.dqkv + ((long long)row0) * 3 * D + h * 64;  // row r of this item: + r * 3D; dQ at +0, dK at +D, dV at +2D
+      TRB(warp, 62, 0);
+      TRI(warp, 0);
+      if (edge) {
+        for (int o = 0; o < 4; ++o)
+          for (int k = 0; k < nblk_ld; ++k) mbar_wait(bars.op(o, k), opar);
+        mbar_wait(bars.cready(it & 1), (uint32_t)(it >> 1) & 1u);  // (this role wrote them, but not necessarily this warp)
+        TRB(warp, 61, 0);
+        const uint32_t sQ = sOp0, sK = sOp0 + opb, sV = sOp0 + 2 * opb, sDO = sOp0 + 3 * opb;
+        const float nle = cst[Tp], dle = cst[320 + Tp];
+        const int g = lane >> 2, t = lane & 3;
+        {
+          // column e (key e against every query i: Q k_e, dO v_e) and row e (query e against every key i: K q_e, V dO_e) as warp-level MMAs
+          uint32_t vbk[8], vbv[8], vbq[8], vbd[8];
+          load_vec_bfrag(sK, Tp, vbk);
+          load_vec_bfrag(sV, Tp, vbv);
+          load_vec_bfrag(sQ, Tp, vbq);
+          load_vec_bfrag(sDO, Tp, vbd);
+#pragma unroll 1
+          for (int rg = q; rg < (Tp >> 4); rg += 4) {
+            const float2 s_c = mv16(sQ, rg * 16, vbk), dp_c = mv16(sDO, rg * 16, vbv), s_r = mv16(sK, rg * 16, vbq), dp_r = mv16(sV, rg * 16, vbd);
+            if (t == 0) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int i = rg * 16 + g + 8 * hh;
+                const float p_c = ex2f(fmaf(hh ? s_c.y : s_c.x, sl2, cst[i]));
+                ev[i] = p_c;
+                ev[288 + i] = p_c * scale * ((hh ? dp_c.y : dp_c.x) - cst[320 + i]);
+                const float p_r = ex2f(fmaf(hh ? s_r.y : s_r.x, sl2, nle));
+                ev[576 + i] = p_r;
+                ev[864 + i] = p_r * scale * ((hh ? dp_r.y : dp_r.x) - dle);
+              }
+            }
+          }
+        }
+        {  // corner (e, e): every warp computes it redundantly (row Tp of an operand is not permuted by the swizzle: Tp % 8 == 0)
+          const uint32_t eo = (uint32_t)Tp * 128u + (uint32_t)lane * 4u;
+          const uint32_t wq = lds32(sQ + eo), wk = lds32(sK + eo), wv = lds32(sV + eo), wd = lds32(sDO + eo);
+          const float s_e = warp_sum(fmaf(bf_lo(wq), bf_lo(wk), bf_hi(wq) * bf_hi(wk)));
+          const float dp_e = warp_sum(fmaf(bf_lo(wd), bf_lo(wv), bf_hi(wd) * bf_hi(wv)));
+          const float p_e = ex2f(fmaf(s_e, sl2, nle)), ds_e = p_e * scale * (dp_e - dle);
+          if (rl == 0) { ev[Tp] = p_e; ev[288 + Tp] = ds_e; ev[576 + Tp] = p_e; ev[864 + Tp] = ds_e; }
+          if (rl >= 1 && rl < 16) { ev[Tp + rl] = 0.f; ev[288 + Tp + rl] = 0.f; ev[576 + Tp + rl] = 0.f; ev[864 + Tp + rl] = 0.f; }  // pad the last 16-group
+          if (q == 0) {  // K_e, Q_e, dO_e as floats for the tile corrections
+            evec[2 * lane] = bf_lo(wk); evec[2 * lane + 1] = bf_hi(wk);
+            evec[64 + 2 * lane] = bf_lo(wq); evec[64 + 2 * lane + 1] = bf_hi(wq);
+            evec[128 + 2 * lane] = bf_lo(wd); evec[128 + 2 * lane + 1] = bf_hi(wd);
+          }
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        {
+          // dQ_e = sum_j dS_ej K_j, dK_e = sum_i dS_ie Q_i, dV_e = sum_i p_ie dO_i over all T tokens: warp q takes the 16-token groups
+          // ks = q (mod 4); lanes 0-3 hold the partial results
+          const int ngrp = (Tp >> 4) + 1;
+#pragma unroll 1
+          for (int pr = 0; pr < 3; ++pr) {
+            const uint32_t buf = pr == 0 ? sK : (pr == 1 ? sQ : sDO);
+            const float* vec = ev + (pr == 0 ? 864 : (pr == 1 ? 288 : 0));
+            float acc[8][4];
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn) acc[nn][0] = acc[nn][1] = acc[nn][2] = acc[nn][3] = 0.f;
+#pragma unroll 1
+            for (int ks = q; ks < ngrp; ks += 4) vm16(buf, ks * 16, vec, acc);
+            if (lane < 4) {
+#pragma unroll
+              for (int nn = 0; nn < 8; ++nn) *reinterpret_cast<float2*>(epart + (pr * 4 + q) * 64 + 8 * nn + 2 * t) = make_float2(acc[nn][0], acc[nn][1]);
+            }
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (q < 3) {  // warp 0: dQ_e, warp 1: dK_e, warp 2: dV_e
+            const float* pp = epart + q * 256 + 2 * lane;
+            const float2 x0 = *reinterpret_cast<const float2*>(pp), x1 = *reinterpret_cast<const float2*>(pp + 64);
+            const float2 x2 = *reinterpret_cast<const float2*>(pp + 128), x3 = *reinterpret_cast<const float2*>(pp + 192);
+            reinterpret_cast<uint32_t*>(out + (long long)Tp * 3 * D + q * D)[lane] = pack_bf2((x0.x + x1.x) + (x2.x + x3.x), (x0.y + x1.y) + (x2.y + x3.y));
+          }
+        }
+        TRB(warp, 61, 1);
+      }
+      // this role no longer reads the item's operands from shared memory
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars.opfree());
+      for (int tc = 0; tc < 2 * ntiles; ++tc) {
+        const int phase = tc >= ntiles ? 1 : 0, tile = tc - phase * ntiles;
+        const int a = phase == 1 ? 2 : (tile & 1);
+        const int row = tile * 128 + rl;
+        mbar_wait(bars.accfull(a), (euse >> a) & 1u);
+        TRB(warp, tc, 0);
+        tcgen05_fence_after();
+        if (tile * 128 + q * 32 < Tp) {
+          uint32_t v0[32], v1[32];
+          const uint32_t col = a == 2 ? 384u : 384u + 64u * a;
+          tmem_ld32(t_lane + col, v0);
+          tmem_ld32(t_lane + col + 32u, v1);
+          tmem_ld_wait();
+          __nv_bfloat16* orow = out + (long long)row * 3 * D;
+          if (phase == 0) {
+            if (row < Tp) {
+              if (edge) store_row64_bf16_axpy(orow, v0, v1, ev[288 + row], evec);            // dQ_i += dS_ie K_e
+              else store_row64_bf16(orow, v0, v1, 1.f);
+            }
+          } else {
+            if (row < Tp) {
+              if (edge) store_row64_bf16_axpy(orow + 2 * D, v0, v1, ev[576 + row], evec + 128);  // dV_j += p_ej dO_e
+              else store_row64_bf16(orow + 2 * D, v0, v1, 1.f);
+            }
+            tmem_ld32(t_lane + col + 64u, v0);
+            tmem_ld32(t_lane + col + 96u, v1);
+            tmem_ld_wait();
+            if (row < Tp) {
+              if (edge) store_row64_bf16_axpy(orow + D, v0, v1, ev[864 + row], evec + 64);       // dK_j += dS_ej Q_e
+              else store_row64_bf16(orow + D, v0, v1, 1.f);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.accfree(a));
+        euse ^= 1u << a;
+        TRB(warp, tc, 1);
+      }
+      TRB(warp, 62, 1);
+      TRI(warp, 1);
     }
   }
   tcgen05_fence_before();
@@ -1364,34 +1438,32 @@ int tc_enabled() {
   return enabled;
 }
 
-template <bool FWD>
-int launch_attn_tc(const void* qkv, const void* dctx, int Nimg, int T, int heads, const AttnParams& p0, cudaStream_t s) {
+int launch_attn_bwd_tc(const void* qkv, const void* dctx, int Nimg, int T, int heads, const AttnParams& p0, cudaStream_t s) {
   AttnParams p = p0;
   p.T = T; p.heads = heads; p.scale = 0.125f;
   p.trace = g_trace;
-  set_geometry(p, T, false);
+  set_geometry(p, T, bwd_edge_enabled());
   const int D = heads * 64;
   CUtensorMap tq, tqt, td, tdt;
   int rc = cg_make_tensor_map_bf16(&tq, qkv, (long long)Nimg * T, 3LL * D, 3LL * D, 64);
   if (rc) return rc;
-  rc = cg_make_tensor_map_bf16(&tqt, qkv, (long long)Nimg * T, 3LL * D, 3LL * D, p.tail_rows);
+  rc = cg_make_tensor_map_bf16(&tqt, qkv, (long long)Nimg * T, 3LL * D, 3LL * D, p.ld_tail);
   if (rc) return rc;
-  td = tq; tdt = tqt;
-  if (!FWD) {
-    rc = cg_make_tensor_map_bf16(&td, dctx, (long long)Nimg * T, D, D, 64);
-    if (rc) return rc;
-    rc = cg_make_tensor_map_bf16(&tdt, dctx, (long long)Nimg * T, D, D, p.tail_rows);
-    if (rc) return rc;
-  }
-  const size_t opb = (size_t)((p.nblk - 1) * 64 + p.tail_rows) * 128;
-  const size_t smem = 1024 + (FWD ? 3 : 4) * opb + (size_t)Depth<FWD>::NPB * (FWD ? TILE_BYTES : 2 * TILE_BYTES) + (FWD ? 1408 : 640 + 256) * 4 + BARS_BYTES;
+  rc = cg_make_tensor_map_bf16(&td, dctx, (long long)Nimg * T, D, D, 64);
+  if (rc) return rc;
+  rc = cg_make_tensor_map_bf16(&tdt, dctx, (long long)Nimg * T, D, D, p.ld_tail);
+  if (rc) return rc;
+  const size_t opb = (size_t)((p.nblk_ld - 1) * 64 + p.ld_tail) * 128;
+  const size_t smem = 1024 + 4 * opb + 4 * (size_t)TILE_BYTES + BWD_FLOATS * 4 + BBARS_BYTES;
+  p.nitems = Nimg * heads;
+  const int grid = p.nitems < cg_num_sms() ? p.nitems : cg_num_sms();  // persistent: one CTA per SM
   static size_t configured[CG_MAX_DEVICES] = {};  // function attributes are per device
   const int dev = cg_device_index();
   if (smem > configured[dev]) {
-    CG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dev] = smem;
   }
-  CG_CUDA(cg_launch_pdl(attn_tc_kernel<FWD>, dim3(heads, Nimg), dim3(AT_THREADS), smem, s, tq, tqt, td, tdt, p));
+  CG_CUDA(cg_launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(AT_THREADS), smem, s, tq, tqt, td, tdt, p));
   return 0;
 }
 
@@ -1433,7 +1505,7 @@ int cg_attention_bwd_tc(const void* qkv, const void* dctx, const float* lse, con
   p.lse = const_cast<float*>(lse);
   p.delta = delta;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
-  return launch_attn_tc<false>(qkv, dctx, Nimg, T, heads, p, s);
+  return launch_attn_bwd_tc(qkv, dctx, Nimg, T, heads, p, s);
 }
 
 // debug only (tools/trace_attn.py): device buffer of 16 * 64 * 8 int64 that CTA (0,0) of the next launches fills with clock64() stamps
