@@ -180,7 +180,10 @@ def call(name, *args):
         ev1.record()
         PROFILE.append((name, args, ev0, ev1))
     launch_count += 1
-    kernel_launches += _KERNELS_PER_CALL.get(name, 1)
+    if name == "cg_attention_bwd" and args[5] <= 272 and os.environ.get("CG_ATTN_TC", "1") != "0":
+        kernel_launches += 1  # one persistent tcgen05 kernel (delta included); the mma.sync path beyond T = 272 is delta + dQ + dK/dV
+    else:
+        kernel_launches += _KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
 
 

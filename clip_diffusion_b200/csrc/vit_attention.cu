@@ -428,7 +428,7 @@ static int pick_warps(int T) {
 
 // vit_attention_tc.cu: tcgen05/TMEM kernels for T <= 272; return 1 when they do not apply
 int cg_attention_fwd_tc(const void* qkv, int Nimg, int T, int heads, void* ctx, float* lse, cudaStream_t s);
-int cg_attention_bwd_tc(const void* qkv, const void* dctx, const float* lse, const float* delta, int Nimg, int T, int heads, void* dqkv, cudaStream_t s);
+int cg_attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, int Nimg, int T, int heads, void* dqkv, cudaStream_t s);
 
 extern "C" int cg_attention_fwd(const void* qkv, int Nimg, int T, int heads, void* ctx, float* lse, void* stream) {
   CG_REQUIRE(qkv && ctx && lse && Nimg > 0 && T > 0 && heads > 0, "cg_attention_fwd: bad arguments");
@@ -456,13 +456,14 @@ extern "C" int cg_attention_bwd(const void* qkv, const void* ctx, const void* dc
   const int Tp = (T + 63) & ~63;
   CG_REQUIRE(Tp <= 640, "cg_attention_bwd: T=%d exceeds the shared-memory resident limit (640)", T);
   cudaStream_t s = cg_stream(stream);
+  {
+    // tcgen05/TMEM path (T <= 272): computes delta = rowsum(dO * O) itself (its epilogue warps, one item ahead)
+    const int rc_tc = cg_attention_bwd_tc(qkv, ctx, dctx, lse, Nimg, T, heads, dqkv, s);
+    if (rc_tc != 1) return rc_tc;
+  }
   const long long rows = (long long)Nimg * T;
   CG_CUDA(cg_launch_pdl(attn_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(ctx),
                         reinterpret_cast<const __nv_bfloat16*>(dctx), T, heads, rows, delta_ws));
-  {
-    const int rc_tc = cg_attention_bwd_tc(qkv, dctx, lse, delta_ws, Nimg, T, heads, dqkv, s);
-    if (rc_tc != 1) return rc_tc;
-  }
   const int W = pick_warps(T);
   const size_t smem_q = (size_t)(2 * Tp) * 128 + (size_t)W * 4096;
   int rc = set_smem(attn_bwd_dq_kernel, smem_q);

@@ -3,40 +3,49 @@
 // Replaces nn.MultiheadAttention inside clip_model.encode_image (clip_diffusion/utils/functional.py:97-102) and its
 // autograd backward (sample.py:199-214).  Scores never leave the SM.
 //
-// One CTA per (image, head); everything the head needs is loaded ONCE by TMA into 128B-swizzled shared memory
-// (forward: Q, K, V; backward: Q, K, V, dO; <= 272 x 64 bf16 each), one mbarrier per 64-row block so the first MMAs
-// start while the rest is still in flight.  The work is cut into BLOCKS of 128 rows x 64 columns of the score matrix
-// and streamed through a pipeline with multi-buffered TMEM (S / dP blocks) and shared-memory staging buffers:
+// Both kernels are PERSISTENT: one CTA per SM walks the (image, head) items, and the block stream -- S / dP blocks of 128 rows x 64
+// columns in multi-buffered TMEM, bf16 P / dS tiles in shared-memory staging buffers, accumulators in TMEM -- runs ACROSS items, so
+// an item's epilogue, the TMEM hand-over and the operand reload overlap the next item's MMAs.  Operands are loaded once per item
+// by TMA into 128B-swizzled shared memory (Q, K, V(, dO); <= 272 x 64 bf16 each), one mbarrier per 64-row block; the next item's
+// tiles are pulled into L2 by a TMA prefetch while the current item runs.  Roles (16 warps):
 //
-//   warps 0-3             tcgen05.mma   FOUR issuer warps (warp-converged loops, elect.sync lane).  With head_dim 64 the MMAs are
-//                                       small (128 x 64 x 16 = 32 tensor-pipe cycles) and a single issuing thread was the bottleneck
-//                                       (measured ~1000 cycles per block).  forward: warps 0 / 1 = S of the even / odd blocks, warp 2 =
-//                                       O += P V; backward: warp 0 = S (S^T), warp 1 = dP (dP^T), warp 2 = dQ | dV, warp 3 = dK.
-//                                       Accumulator MMAs take the staged operand as K-major A and V / K / dO / Q as MN-major B.
-//   warps 4-7 / 8-11      softmax       two warpgroups, block g goes to warpgroup g & 1; a thread owns one row (= one TMEM lane):
-//                                       tcgen05.ld, exp2 / dS arithmetic in registers, bf16 result written to the staging buffer in the
-//                                       K-major 128B-swizzled operand layout.  A tile with ONE real row (T = 128 k + 1: the ViT-L/14
-//                                       sequence 257) is spread over the lanes of its warp through shared memory instead.
-//   warps 12-15           epilogue      tcgen05.ld of the finished accumulators -> bf16 -> HBM
-//   warp 0 lane 0         TMA producer (before the CTA-wide sync), warp 2 TMEM allocation
-//
-// All smem / TMEM operand forms are the ones vit_gemm.cu and the round-1 forward validated: K-major SW128 A and B, MN-major SW128 B
-// with N = 64.  Every mbarrier waiter sees every phase of its barrier (a parity wait is only sound then): warps without real rows
-// still arrive in step, and no consumer ever skips a use of a shared buffer.
+//   MMA issuers (warp-converged loops, elect.sync lane; with head_dim 64 a single issuing thread was the bottleneck)
+//       forward   warps 0 / 1: S = Q K^T of the even / odd blocks    warp 2: O += P V    warp 3: TMA producer
+//       backward  warp 0: S (S^T)   warp 1: dP (dP^T)   warp 2: dQ | dV   warp 3: dK + TMA producer
+//   softmax   warps 4-7 / 8-11: two warpgroups, block g goes to warpgroup g & 1; a thread owns one row (= one TMEM lane): tcgen05.ld,
+//             exp2 / dS arithmetic in registers, bf16 result written to the staging buffer in the K-major 128B-swizzled operand
+//             layout; the forward reads each S block from TMEM twice to stay inside 128 registers (a spill costs an L2 round trip
+//             here: shared memory leaves ~28 KB of L1)
+//   epilogue  warps 12-15: finished accumulators -> bf16 -> HBM; the backward's per-token constants (-lse log2e, delta = rowsum(dO O)
+//             computed here from the two global tensors, one item ahead); the edge token
 //
 //   forward   ONE pass, online softmax without a row-maximum pre-pass: each warpgroup keeps its own reference maximum and row sum
 //             and accumulates ITS blocks into ITS OWN O accumulator; the reference only moves when a block exceeds it by 2^8 (then
-//             the accumulator is rescaled in TMEM: tcgen05.ld / tcgen05.st); the epilogue merges the two partial results.
+//             the accumulator is rescaled in TMEM: tcgen05.ld / tcgen05.st); the epilogue merges the partial results.
 //   backward  phase A (lane = query):  S = Q K^T, dP = dO V^T, dS = P (dP - delta) scale, dQ += dS K
 //             phase B (lane = key):    S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
 //             P is recomputed from the saved log-sum-exp; two orientations instead of a transposed smem operand, no atomics,
 //             deterministic.  Rows / columns beyond T are masked (tail block only) or never stored.
 //
-// Measured on B200 (profiles/r02_kernel_rooflines.txt, r02_ncu_vit_kernels_digest.txt), T = 257 x 64 images x 16 heads: forward 102 us, backward 214 us per layer (round 1
-// mma.sync kernels: 104 / 349).  A softmax warp spends ~2900 cycles per 64-column block of which the MUFU-bound share is 1024 (two warps
-// per SM sub-partition, 8 cycles per MUFU.EX2 warp instruction, measured with tools/probes/mufu_probe.cu): the tcgen05.ld latency, the
-// serial max chain, the proxy fence and the barrier round trips of the two warps of a sub-partition run in lock step and leave the MUFU
-// idle.  More softmax warps per sub-partition (register budget: 512 threads x 128) is the next step.
+// Edge token.  T = 64 m + 1 (ViT-L/14: 16 x 16 patches + class token = 257) would leave the pipeline with a 1-row tile and a 1-column
+// block per tile, each costing a full S -> softmax -> MMA round trip (25-30% of an item).  The LAST token is therefore kept out of
+// the pipeline, which then sees only full tiles and blocks: its row and column of the score matrix are matrix-vector products, done by
+// the epilogue warps with warp-level m16n8k16 MMAs on the TMA-written tiles (ldmatrix), and folded in when a tile is written
+// (forward: a third partial result of the online-softmax merge; backward: rank-1 corrections dQ_i += dS_ie K_e, dK_j += dS_ej Q_e,
+// dV_j += p_ej dO_e, plus the three reductions that give row e of dQ, dK, dV).
+//
+// All smem / TMEM operand forms are the ones vit_gemm.cu validated: K-major SW128 A and B, MN-major SW128 B with N = 64.  Every
+// mbarrier waiter sees every phase of its barrier (a parity wait is only sound then): warps without real rows still arrive in
+// step, no consumer skips a use of a shared buffer, and the issuers observe all operand barriers of every item.
+//
+// Measured on B200 (profiles/r02_kernel_rooflines.txt, r02_ncu_vit_kernels_digest.txt, time lines with `make trace` +
+// tools/trace_attn.py), T = 257 x 64 images x 16 heads, per layer: forward 70 us, backward (incl. delta) 185 us; round 1 mma.sync
+// kernels: 104 / 349 + 24; first tcgen05 version of this round (one CTA per item, 1-row tile in the pipeline): 102 / 214 + 24.  In SM
+// cycles per item: forward 29 000 -> 14 500, backward 61 000 -> 36 000.  What bounds them now: a softmax warp spends ~2400 cycles per
+// 64-column block (MUFU-bound share 1024: two warps per SM sub-partition, 8 cycles per MUFU.EX2 warp instruction), i.e. ~10 000
+// cycles per item and warpgroup in the forward; the forward's epilogue warps (tile merges + ~9000 cycles of edge work per item) are
+// its critical resource; the backward pays ~4000 cycles per item for the single-buffered operand reload (220 KB of shared memory
+// are in use).  Under load the GPU runs these kernels at 1.45-1.8 GHz (sw_power_cap), not at 1.965.
 #include <stdlib.h>
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -65,10 +74,6 @@ __device__ __forceinline__ float warp_max_f(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ void st_shared_b16(uint32_t a, float v) {
-  const __nv_bfloat16 b = __float2bfloat16_rn(v);
-  asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(*reinterpret_cast<const unsigned short*>(&b)) : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -89,15 +94,6 @@ __device__ __forceinline__ uint32_t idesc_bf16(int n, bool b_mn_major) {
 __device__ __forceinline__ void st_shared_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-// 32 consecutive columns [c0, c0+32) (c0 = 0 or 32) of row r of a [128 x 64] bf16 K-major 128B-swizzled tile: w = 16 packed pairs
-__device__ __forceinline__ void stage_store32(uint32_t tile_base, int r, int c0, const uint32_t* w) {
-  const uint32_t rowb = tile_base + (uint32_t)r * 128u;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t chunk = (uint32_t)(((c0 >> 3) + j) ^ (r & 7));
-    st_shared_v4(rowb + (chunk << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-  }
-}
 __device__ __forceinline__ void st256g(void* p, const uint32_t* w) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]),
                "r"(w[6]), "r"(w[7])
@@ -115,12 +111,7 @@ __device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const uint3
   for (int j = 0; j < 4; ++j) st256g(dst + 16 * j, w + 8 * j);
 }
 
-// ---- CUDA-core helpers of the "edge token" path (T = 64 m + 1: the last token is handled outside the tensor-core pipeline)
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-  return v;
-}
+// ---- shared-memory / bf16 helpers of the "edge token" path (T = 64 m + 1: the last token is handled outside the tensor-core pipeline)
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -128,58 +119,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
 }
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
-__device__ __forceinline__ void unpack8(const uint4 u, float* f) {
-  f[0] = bf_lo(u.x); f[1] = bf_hi(u.x); f[2] = bf_lo(u.y); f[3] = bf_hi(u.y);
-  f[4] = bf_lo(u.z); f[5] = bf_hi(u.z); f[6] = bf_lo(u.w); f[7] = bf_hi(u.w);
-}
-__device__ __forceinline__ float dot8(const uint4 a, const float* f, float acc) {
-  acc = fmaf(bf_lo(a.x), f[0], acc); acc = fmaf(bf_hi(a.x), f[1], acc); acc = fmaf(bf_lo(a.y), f[2], acc); acc = fmaf(bf_hi(a.y), f[3], acc);
-  acc = fmaf(bf_lo(a.z), f[4], acc); acc = fmaf(bf_hi(a.z), f[5], acc); acc = fmaf(bf_lo(a.w), f[6], acc); acc = fmaf(bf_hi(a.w), f[7], acc);
-  return acc;
-}
-// dot product of row `r` of a 128B-swizzled [rows x 64] bf16 operand buffer with a 64-float vector in registers
-__device__ __forceinline__ float dot_row64(uint32_t buf, int r, const float* f) {
-  const uint32_t rowb = buf + (uint32_t)r * 128u, x = (uint32_t)(r & 7);
-  float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; c += 2) {
-    a0 = dot8(lds128(rowb + (((uint32_t)c ^ x) << 4)), f + 8 * c, a0);
-    a1 = dot8(lds128(rowb + (((uint32_t)(c + 1) ^ x) << 4)), f + 8 * c + 8, a1);
-  }
-  return a0 + a1;
-}
 // dot product of two packed groups of 8 bf16
 __device__ __forceinline__ float dot8p(const uint4 a, const uint4 b, float acc) {
   acc = fmaf(bf_lo(a.x), bf_lo(b.x), acc); acc = fmaf(bf_hi(a.x), bf_hi(b.x), acc); acc = fmaf(bf_lo(a.y), bf_lo(b.y), acc); acc = fmaf(bf_hi(a.y), bf_hi(b.y), acc);
   acc = fmaf(bf_lo(a.z), bf_lo(b.z), acc); acc = fmaf(bf_hi(a.z), bf_hi(b.z), acc); acc = fmaf(bf_lo(a.w), bf_lo(b.w), acc); acc = fmaf(bf_hi(a.w), bf_hi(b.w), acc);
   return acc;
-}
-// dot product of row ra of buffer A with row rb of buffer B (both 128B-swizzled [rows x 64] bf16).  Deliberately a ROLLED loop: the edge
-// paths run once per tile and must stay small -- the forward kernel slowed down by 30-60% in every role when its code grew from 54 KB to
-// 99 KB (instruction-cache misses), measured with the time-line probes.
-__device__ __forceinline__ float dot_rows(uint32_t bufa, int ra, uint32_t bufb, int rb) {
-  const uint32_t pa = bufa + (uint32_t)ra * 128u, xa = (uint32_t)(ra & 7) << 4, pb = bufb + (uint32_t)rb * 128u, xb = (uint32_t)(rb & 7) << 4;
-  float acc = 0.f;
-#pragma unroll 1
-  for (uint32_t c = 0; c < 128u; c += 16u) acc = dot8p(lds128(pa + (c ^ xa)), lds128(pb + (c ^ xb)), acc);
-  return acc;
-}
-// the same, unrolled with two accumulators (16 loads in flight)
-__device__ __forceinline__ float dot_rows2(uint32_t bufa, int ra, uint32_t bufb, int rb) {
-  const uint32_t pa = bufa + (uint32_t)ra * 128u, xa = (uint32_t)(ra & 7) << 4, pb = bufb + (uint32_t)rb * 128u, xb = (uint32_t)(rb & 7) << 4;
-  float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-  for (uint32_t c = 0; c < 128u; c += 32u) {
-    a0 = dot8p(lds128(pa + (c ^ xa)), lds128(pb + (c ^ xb)), a0);
-    a1 = dot8p(lds128(pa + ((c + 16u) ^ xa)), lds128(pb + ((c + 16u) ^ xb)), a1);
-  }
-  return a0 + a1;
-}
-// row `r` (any row: the swizzle is undone) of such a buffer -> 64 floats
-__device__ __forceinline__ void load_row64(uint32_t buf, int r, float* f) {
-  const uint32_t rowb = buf + (uint32_t)r * 128u, x = (uint32_t)(r & 7);
-#pragma unroll
-  for (int c = 0; c < 8; ++c) unpack8(lds128(rowb + (((uint32_t)c ^ x) << 4)), f + 8 * c);
 }
 
 struct AttnParams {
@@ -190,7 +134,8 @@ struct AttnParams {
   float scale;
   __nv_bfloat16* ctx;        // forward out [Nimg*T, D]
   float* lse;                // [Nimg, heads, T]  (forward out, backward in)
-  const float* delta;        // backward in [Nimg, heads, T]
+  const __nv_bfloat16* ctx_in;   // backward in: forward output [Nimg*T, D] and its gradient [Nimg*T, D] (delta = rowsum(dO * O) is computed
+  const __nv_bfloat16* dctx_in;  // by the epilogue warps)
   __nv_bfloat16* dqkv;       // backward out [Nimg*T, 3D]
   long long* trace;          // debug: clock64() time line of CTA (0,0) (tools/trace_attn.py); nullptr in production
 };
@@ -623,7 +568,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     const int rl = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = p.scale * LOG2E_F;
-    const int tail_cols = Tp - (nblk - 1) * 64, tail_cols16 = p.tail_rows;
+    const int tail_cols = Tp - (nblk - 1) * 64;
     const uint32_t sx = (uint32_t)(rl & 7) << 4;  // 128B swizzle of this thread's row of a staged tile: 16-byte chunk c sits at (c << 4) ^ sx
     uint32_t wuse0 = 0, wuse1 = 0;  // uses of this warpgroup's two accumulator slots (tile parity 0 / 1)
     int it = 0, gg0 = 0;
@@ -1243,13 +1188,29 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     const float scale = p.scale, sl2 = p.scale * LOG2E_F;
     uint32_t euse = 0;  // bit a: parity of the use count of accumulator slot a
     auto load_consts = [&](int item, int par) {
+      // per-token constants of an item: -lse log2e, and delta_i = sum_d dO_i[d] O_i[d] straight from the two global tensors (the
+      // separate row-dot-product kernel cost 24 us per layer; these warps have the slack)
       const int n = item / heads, h = item - n * heads;
       const float* lb = p.lse + ((long long)n * heads + h) * T;
-      const float* db = p.delta + ((long long)n * heads + h) * T;
+      const __nv_bfloat16* ob = p.ctx_in + ((long long)n * T) * D + h * 64;
+      const __nv_bfloat16* gb = p.dctx_in + ((long long)n * T) * D + h * 64;
       float* c = csts + par * 640;
       for (int i = rl; i < 320; i += 128) {
-        c[i] = i < T ? -lb[i] * LOG2E_F : -INFINITY;
-        c[320 + i] = i < T ? db[i] : 0.f;
+        float dl = 0.f, nl = -INFINITY;
+        if (i < T) {
+          const uint4* o4 = reinterpret_cast<const uint4*>(ob + (long long)i * D);
+          const uint4* g4 = reinterpret_cast<const uint4*>(gb + (long long)i * D);
+          uint4 xo[8], xg[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { xo[k] = __ldg(o4 + k); xg[k] = __ldg(g4 + k); }
+          float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) { d0 = dot8p(xo[k], xg[k], d0); d1 = dot8p(xo[k + 1], xg[k + 1], d1); }
+          dl = d0 + d1;
+          nl = -lb[i] * LOG2E_F;
+        }
+        c[i] = nl;
+        c[320 + i] = dl;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bars.cready(par));
@@ -1498,12 +1459,12 @@ int cg_attention_fwd_tc(const void* qkv, int Nimg, int T, int heads, void* ctx, 
   return 0;
 }
 
-// delta[n,h,q] = rowsum(dO * O) must already be in `delta` (attn_delta_kernel, vit_attention.cu)
-int cg_attention_bwd_tc(const void* qkv, const void* dctx, const float* lse, const float* delta, int Nimg, int T, int heads, void* dqkv, cudaStream_t s) {
+int cg_attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, int Nimg, int T, int heads, void* dqkv, cudaStream_t s) {
   if (T > 272 || !tc_enabled()) return 1;
   AttnParams p = {};
   p.lse = const_cast<float*>(lse);
-  p.delta = delta;
+  p.ctx_in = reinterpret_cast<const __nv_bfloat16*>(ctx);
+  p.dctx_in = reinterpret_cast<const __nv_bfloat16*>(dctx);
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   return launch_attn_bwd_tc(qkv, dctx, Nimg, T, heads, p, s);
 }
