@@ -176,7 +176,8 @@ int cg_gemm_bf16_tn(const void* A, const void* B, int M, int N, int K, int64_t l
 /* Fused multi-head attention over packed qkv [Nimg*T, 3*D] bf16 (q | k | v, head h at column h*64), head_dim 64,
  * softmax scale 1/8.  ctx [Nimg*T, D] bf16, lse [Nimg, heads, T] fp32. */
 int cg_attention_fwd(const void* qkv, int Nimg, int T, int heads, void* ctx, float* lse, void* stream);
-/* dgrad: dctx [Nimg*T, D] bf16 -> dqkv [Nimg*T, 3*D] bf16 (recomputes P from q,k,lse). */
+/* dgrad: dctx [Nimg*T, D] bf16 -> dqkv [Nimg*T, 3*D] bf16 (recomputes P from q,k,lse).  delta_ws [Nimg, heads, T] fp32 is scratch for
+ * rowsum(dO * O): written by the T > 272 (mma.sync) path only; the tcgen05 path (T <= 272) keeps those sums on chip. */
 int cg_attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, int Nimg, int T, int heads,
                      void* dqkv, float* delta_ws, void* stream);
 
