@@ -322,7 +322,7 @@ __device__ __forceinline__ float2 fwd_edge_token_a(uint32_t sQ, uint32_t sK, int
   return make_float2(rl < Tp ? sev[rl] : -INFINITY, 128 + rl < Tp ? sev[128 + rl] : -INFINITY);
 }
 __device__ __forceinline__ void fwd_edge_token_b(uint32_t sV, int Tp, float* pvec, float* vedge, __nv_bfloat16* ctx_row, float* lse_out, long long* tr) {
-  const int rl = threadIdx.x & 127, q = rl >> 5, lane = rl & 31, t = lane & 3;
+  const int rl = threadIdx.x & 127, q = rl >> 5, lane = rl & 31;
   float* red = pvec + 288;
   float* part = pvec + 296;   // [4][64]
   if (rl < 32) {
@@ -350,16 +350,25 @@ __device__ __forceinline__ void fwd_edge_token_b(uint32_t sV, int Tp, float* pve
   l = (red[4] + red[5]) + (red[6] + red[7]);
   TRE(3);
   {
-    // O_e = sum_j p_j V[j]: warp q takes the key groups ks = q (mod 4)
-    float acc[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-#pragma unroll 1
-    for (int ks = q; ks < ngrp; ks += 4) vm16(sV, ks * 16, pvec, acc);
-    if (lane < 4) {
-#pragma unroll
-      for (int n = 0; n < 8; ++n) *reinterpret_cast<float2*>(part + q * 64 + 8 * n + 2 * t) = make_float2(acc[n][0], acc[n][1]);
+    // O_e = sum_j p_j V[j] on CUDA cores: warp q takes the keys j = q (mod 4), lane owns d = 2 lane, 2 lane + 1 (one 32-bit word of a V
+    // row: conflict free).  (As 16-key MMA steps this took twice as long: legacy mma.sync next to running tcgen05 MMAs, ~700 cycles a step.)
+    const int T = Tp + 1;
+    const uint32_t vcol = ((uint32_t)(lane >> 2) << 4), vin = (uint32_t)(lane & 3) << 2;
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    int j = q;
+#pragma unroll 4
+    for (; j + 4 < T; j += 8) {
+      const uint32_t va = lds32(sV + (uint32_t)j * 128u + (vcol ^ ((uint32_t)(j & 7) << 4)) + vin);
+      const uint32_t vb = lds32(sV + (uint32_t)(j + 4) * 128u + (vcol ^ ((uint32_t)((j + 4) & 7) << 4)) + vin);
+      const float pa = pvec[j], pb = pvec[j + 4];
+      o0 = fmaf(pa, bf_lo(va), o0); o1 = fmaf(pa, bf_hi(va), o1);
+      o2 = fmaf(pb, bf_lo(vb), o2); o3 = fmaf(pb, bf_hi(vb), o3);
     }
+    if (j < T) {
+      const uint32_t va = lds32(sV + (uint32_t)j * 128u + (vcol ^ ((uint32_t)(j & 7) << 4)) + vin);
+      o0 = fmaf(pvec[j], bf_lo(va), o0); o1 = fmaf(pvec[j], bf_hi(va), o1);
+    }
+    *reinterpret_cast<float2*>(part + q * 64 + 2 * lane) = make_float2(o0 + o2, o1 + o3);
   }
   TRE(4);
   asm volatile("bar.sync 2, 128;" ::: "memory");
