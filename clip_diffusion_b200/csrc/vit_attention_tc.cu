@@ -878,7 +878,7 @@ struct BBars {
   __device__ __forceinline__ uint32_t tmem_slot() const { return base + 312u; }
 };
 constexpr uint32_t BBARS_BYTES = 320 + 16;
-// float scratch: constants [2][640] (-lse log2e [320], delta [320]); edge vectors [4][288] (p_ie, dS_ie, p_ej, dS_ej); K_e, Q_e, dO_e as
+// float scratch: constants [2][640] (-lse log2e [320], -scale delta [320]); edge vectors [4][288] (p_ie, dS_ie, p_ej, dS_ej); K_e, Q_e, dO_e as
 // floats [3][64]; partial sums [3][4][32] float2
 constexpr uint32_t BWD_FLOATS = 1280 + 1152 + 192 + 768;
 
@@ -1094,7 +1094,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     int it = 0, gg0 = 0;
     for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it, gg0 += G) {
       mbar_wait(bars.cready(it & 1), (uint32_t)(it >> 1) & 1u);
-      const float* cst = csts + (it & 1) * 640;  // [0, 320): -lse log2e (-inf beyond T), [320, 640): delta
+      const float* cst = csts + (it & 1) * 640;  // [0, 320): -lse log2e (-inf beyond T), [320, 640): -scale delta
       float rc0 = 0.f, rc1 = 0.f;  // phase A: -lse * log2e and delta of this thread's query row
       int phase = 0, tile = 0, blk = wg, cur_tile = -1;
       while (blk >= nblk) { blk -= nblk; if (++tile == ntiles) { tile = 0; ++phase; } }
@@ -1103,7 +1103,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         if (phase == 0 && tile != cur_tile) {
           const int row = tile * 128 + rl;
           rc0 = row < Tp ? cst[row] : 0.f;
-          rc1 = row < Tp ? cst[320 + row] : 0.f;
+          rc1 = row < Tp ? cst[320 + row] : 0.f;  // -scale delta: dS = P (scale dP - scale delta) is one FFMA + one FMUL per element
           cur_tile = tile;
         }
         const bool wvalid = tile * 128 + q * 32 < Tp;  // warp-uniform: this warp has at least one real row
@@ -1146,7 +1146,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
                 for (int j = 0; j < 8; ++j) {
                   float p0 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j]), sl2, rc0)), p1 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j + 1]), sl2, rc0));
                   if (tail) { if (16 * pc + 2 * j >= ncols) p0 = 0.f; if (16 * pc + 2 * j + 1 >= ncols) p1 = 0.f; }
-                  w0[j] = pack_bf2(p0 * scale * (__uint_as_float(dv[cur][2 * j]) - rc1), p1 * scale * (__uint_as_float(dv[cur][2 * j + 1]) - rc1));
+                  w0[j] = pack_bf2(p0 * fmaf(__uint_as_float(dv[cur][2 * j]), scale, rc1), p1 * fmaf(__uint_as_float(dv[cur][2 * j + 1]), scale, rc1));
                 }
               } else {
                 const float* nl = cst + blk * 64 + 16 * pc;  // per-query constants: broadcast reads
@@ -1157,7 +1157,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
                   float p0 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j]), sl2, l2.x)), p1 = ex2f(fmaf(__uint_as_float(sv[cur][2 * j + 1]), sl2, l2.y));
                   if (tail) { if (16 * pc + 2 * j >= ncols) p0 = 0.f; if (16 * pc + 2 * j + 1 >= ncols) p1 = 0.f; }
                   w0[j] = pack_bf2(p0, p1);
-                  w1[j] = pack_bf2(p0 * scale * (__uint_as_float(dv[cur][2 * j]) - d2.x), p1 * scale * (__uint_as_float(dv[cur][2 * j + 1]) - d2.y));
+                  w1[j] = pack_bf2(p0 * fmaf(__uint_as_float(dv[cur][2 * j]), scale, d2.x), p1 * fmaf(__uint_as_float(dv[cur][2 * j + 1]), scale, d2.y));
                 }
               }
               if (!waited) { mbar_wait(bars.pfree(pb), (puse & 1u) ^ 1u); waited = true; }  // staging buffer free again
@@ -1219,7 +1219,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
           nl = -lb[i] * LOG2E_F;
         }
         c[i] = nl;
-        c[320 + i] = dl;
+        c[320 + i] = -p.scale * dl;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bars.cready(par));
@@ -1241,7 +1241,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         mbar_wait(bars.cready(it & 1), (uint32_t)(it >> 1) & 1u);  // (this role wrote them, but not necessarily this warp)
         TRB(warp, 61, 0);
         const uint32_t sQ = sOp0, sK = sOp0 + opb, sV = sOp0 + 2 * opb, sDO = sOp0 + 3 * opb;
-        const float nle = cst[Tp], dle = cst[320 + Tp];
+        const float nle = cst[Tp], dle = cst[320 + Tp];  // (-scale delta_e)
         const int g = lane >> 2, t = lane & 3;
         {
           // column e (key e against every query i: Q k_e, dO v_e) and row e (query e against every key i: K q_e, V dO_e) as warp-level MMAs
@@ -1259,10 +1259,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
                 const int i = rg * 16 + g + 8 * hh;
                 const float p_c = ex2f(fmaf(hh ? s_c.y : s_c.x, sl2, cst[i]));
                 ev[i] = p_c;
-                ev[288 + i] = p_c * scale * ((hh ? dp_c.y : dp_c.x) - cst[320 + i]);
+                ev[288 + i] = p_c * fmaf(hh ? dp_c.y : dp_c.x, scale, cst[320 + i]);
                 const float p_r = ex2f(fmaf(hh ? s_r.y : s_r.x, sl2, nle));
                 ev[576 + i] = p_r;
-                ev[864 + i] = p_r * scale * ((hh ? dp_r.y : dp_r.x) - dle);
+                ev[864 + i] = p_r * fmaf(hh ? dp_r.y : dp_r.x, scale, dle);
               }
             }
           }
@@ -1272,7 +1272,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
           const uint32_t wq = lds32(sQ + eo), wk = lds32(sK + eo), wv = lds32(sV + eo), wd = lds32(sDO + eo);
           const float s_e = warp_sum(fmaf(bf_lo(wq), bf_lo(wk), bf_hi(wq) * bf_hi(wk)));
           const float dp_e = warp_sum(fmaf(bf_lo(wd), bf_lo(wv), bf_hi(wd) * bf_hi(wv)));
-          const float p_e = ex2f(fmaf(s_e, sl2, nle)), ds_e = p_e * scale * (dp_e - dle);
+          const float p_e = ex2f(fmaf(s_e, sl2, nle)), ds_e = p_e * fmaf(dp_e, scale, dle);
           if (rl == 0) { ev[Tp] = p_e; ev[288 + Tp] = ds_e; ev[576 + Tp] = p_e; ev[864 + Tp] = ds_e; }
           if (rl >= 1 && rl < 16) { ev[Tp + rl] = 0.f; ev[288 + Tp + rl] = 0.f; ev[576 + Tp + rl] = 0.f; ev[864 + Tp + rl] = 0.f; }  // pad the last 16-group
           if (q == 0) {  // K_e, Q_e, dO_e as floats for the tile corrections
