@@ -1,4 +1,8 @@
-"""Debug: per-role clock64() time line of CTA (0,0) of the tcgen05 attention kernels (vit_attention_tc.cu, TR() probes)."""
+"""Debug: per-role clock64() time line of CTA 0 of the persistent tcgen05 attention kernels (vit_attention_tc.cu, TRF / TRB / TRI probes;
+third item of the CTA, plus the start / end of every item).  Needs the probe build:
+    make -C clip_diffusion_b200/csrc trace
+    CLIPGUIDE_B200_LIB=$PWD/clip_diffusion_b200/csrc/libclipguide_b200_trace.so python tools/trace_attn.py 64 257 fwd|bwd
+Output format: see the header lines of profiles/r02_attention_timeline_*.txt."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
