@@ -101,9 +101,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def summary(self, t0, t1, t_end=None):
+    def stop(self):
         if self.proc is not None:
             self.proc.terminate()
+            self.proc = None
+
+    def summary(self, t0, t1, t_end=None):
+        self.stop()
         rows = ([r for ts, r in self.rows if t0 <= ts <= t1 and len(r) >= 7] or [r for ts, r in self.rows if t0 <= ts <= (t_end or t1) and len(r) >= 7]
                 or [r for _, r in self.rows[-3:] if len(r) >= 7])
         if not rows:
@@ -408,6 +412,7 @@ def main():
             x = step(x, i)["sample"]
             i = next_i(i)
         e1.record()
+        res["host_enqueue_ms"] = (time.time() - wall0) * 1e3 / K  # host time to ISSUE a step (the GPU runs behind it): the floor of the e2e step
         barrier()
         if use_range:
             torch.cuda.profiler.stop()
@@ -418,6 +423,8 @@ def main():
             res["launches"] += K * unet.own_kernels_per_replay
         if not profile:
             return res
+        if clocks is not None and os.environ.get("CG_BENCH_CLOCKS_ALL_REGIONS") != "1":
+            clocks.stop()  # nvidia-smi polling takes driver locks: harmless while launches are queued ahead, visible in the synchronised region below
         # ---- timed region 2: end to end through host buffers ------------------------------------------
         barrier()
         e0.record()
@@ -476,6 +483,7 @@ def main():
         "steps_per_s": value,
         "e2e": {"value": cuts_per_step * e2e, "unit": "cutouts/s", "steps_per_s": e2e, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": main_res["launches"],
+        "host_enqueue_ms_per_step": main_res.get("host_enqueue_ms"),
         "clocks": main_res["clocks"],
         "roofline": roof,
     }

@@ -122,6 +122,11 @@ class VisionTransformerB200:
             self.blocks.append(blk)
         self._ws = {}  # persistent activation workspaces per batch size (stable addresses => TMA descriptor cache hits)
         self._generation = 0  # bumped by every forward: the saved activations live in the shared workspace, not in an autograd ctx
+        # CUDA graphs: a tower pass is ~7 C-ABI calls per layer and direction on fixed buffers; issuing them one by one costs the host
+        # ~12 ms per step for ViT-L/14 (measured: bench.py `host_enqueue_ms_per_step`), which bounds the small configurations and the
+        # end-to-end step.  The first pass of a batch size runs eagerly (function attributes, descriptor cache, scratch allocation), the
+        # second is captured, later ones are replayed.  CG_VIT_GRAPHS=0 (or use_graphs = False) keeps every pass eager.
+        self.use_graphs = os.environ.get("CG_VIT_GRAPHS", "1") != "0"
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, n):
@@ -143,6 +148,10 @@ class VisionTransformerB200:
             # backward
             "dx": f32(M, D), "dxb": b16(M, D), "dy": f32(n, D), "du": b16(M, 4 * D), "dh": f32(M, D), "dctx": b16(M, D),
             "dqkv": b16(M, 3 * D), "delta": f32(n, self.heads, T), "dx0": f32(M, D), "dtok": b16(n * (T - 1), D),
+            # static input / output buffers of the (graph-replayable) passes
+            "patches": b16(n, self.grid ** 2, self.kpad), "emb": f32(n, self.output_dim), "demb": f32(n, self.output_dim),
+            "dpatch": f32(n, self.grid ** 2, self.kpad),
+            "graphs": {},
         }
         if len(self._ws) >= 4:  # bound the footprint when batch sizes keep changing (cut schedules)
             self._ws.pop(next(iter(self._ws)))
@@ -158,8 +167,52 @@ class VisionTransformerB200:
         if patches.shape[1] != g2 or patches.shape[2] != self.kpad or patches.dtype != torch.bfloat16:
             raise ValueError("expected bf16 patches of shape [N, %d, %d], got %s %s" % (g2, self.kpad, tuple(patches.shape), patches.dtype))
         ws = self._workspace(n)
+        if patches.data_ptr() != ws["patches"].data_ptr():
+            ws["patches"].copy_(patches)
+        self._run_pass(ws, "fwd", lambda: self._forward_body(ws, n))
+        self._last_n = n
+        self._generation += 1
+        ws["generation"] = self._generation
+        return ws["emb"].clone()
+
+    def _run_pass(self, ws, key, body):
+        """Run one tower pass on the workspace buffers: eagerly, or as a CUDA graph (first call eager, second captured, then replayed).
+        Per-call profiling (bench.py's kernel rooflines) needs the individual launches, so it forces the eager path."""
+        if not self.use_graphs or _lib.PROFILE is not None:
+            body()
+            return
+        st = ws["graphs"].setdefault(key, {"calls": 0, "graph": None, "launches": 0, "failed": False})
+        if st["failed"]:
+            body()
+            return
+        if st["graph"] is None:
+            st["calls"] += 1
+            if st["calls"] == 1:
+                body()
+                return
+            k0, c0 = _lib.kernel_launches, _lib.launch_count
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    body()
+            except Exception as exc:  # keep the product path alive, loudly: the eager launches are the same kernels
+                import warnings
+                st["failed"] = True
+                warnings.warn("CUDA graph capture of the %s %s pass failed (%s); this tower keeps issuing its kernels one by one" % (self.name, key, exc))
+                torch.cuda.synchronize()
+                body()
+                return
+            st["graph"], st["launches"], st["calls_per_pass"] = graph, _lib.kernel_launches - k0, _lib.launch_count - c0
+            _lib.kernel_launches, _lib.launch_count = k0, c0  # capturing launched nothing; the replay below counts
+        st["graph"].replay()
+        _lib.kernel_launches += st["launches"]
+        _lib.launch_count += st["calls_per_pass"]
+
+    def _forward_body(self, ws, n):
+        g2, D, T, E = self.grid ** 2, self.width, self.tokens, self.output_dim
+        M = n * T
         P, C = _lib.ptr, _lib.call
-        a = patches.reshape(n * g2, self.kpad)
+        a = ws["patches"].view(n * g2, self.kpad)
         gemm_bf16_tn(a, self.w_patch, _lib.EPI_PATCH_POS_F32, out=ws["x0"], pos=self.pos, g2=g2)
         C("cg_vit_set_cls_rows", P(self.cls), P(self.pos), n, T, D, P(ws["x0"]))
         x = ws["layers"][0]["x_in"] if self.layers else ws["x_out"]
@@ -175,12 +228,7 @@ class VisionTransformerB200:
             gemm_bf16_tn(ws["hg"], blk["w_proj"], _lib.EPI_BIAS_RESID_F32, bias=blk["b_proj"], out=x_next, aux=L["x_mid"])
         # ln_post on the class-token rows (row stride T*D), then the projection
         C("cg_layernorm_fwd", P(ws["x_out"]), P(self.ln_post[0]), P(self.ln_post[1]), n, D, T * D, None, P(ws["y"]), P(ws["meanp"]), P(ws["rstdp"]))
-        emb = torch.empty(n, E, device=self.device, dtype=torch.float32)
-        C("cg_vit_proj_fwd", P(ws["y"]), P(self.proj), n, D, E, P(emb))
-        self._last_n = n
-        self._generation += 1
-        ws["generation"] = self._generation
-        return emb
+        C("cg_vit_proj_fwd", P(ws["y"]), P(self.proj), n, D, E, P(ws["emb"]))
 
     # ------------------------------------------------------------------ backward (input gradient only)
     def backward_patches(self, demb, generation=None):
@@ -201,11 +249,16 @@ class VisionTransformerB200:
                 "forward (generation %d) and its backward (workspace now holds generation %d).  The tower keeps ONE set of saved "
                 "activations per batch size; differentiate each embedding batch before embedding the next one of the same size "
                 "(sample.py:199-214 does exactly that)." % (n, generation, ws["generation"]))
+        ws["demb"].copy_(demb)
+        self._run_pass(ws, "bwd", lambda: self._backward_body(ws, n))
+        # the gradient buffer belongs to the workspace: consume it before the next backward of the same batch size (sample.py does)
+        return ws["dpatch"]
+
+    def _backward_body(self, ws, n):
         g2, D, T, E = self.grid ** 2, self.width, self.tokens, self.output_dim
         M = n * T
         P, C = _lib.ptr, _lib.call
-        demb = demb.contiguous().float()
-        C("cg_vit_proj_bwd", P(demb), P(self.proj), n, D, E, P(ws["dy"]))
+        C("cg_vit_proj_bwd", P(ws["demb"]), P(self.proj), n, D, E, P(ws["dy"]))
         ws["dx"].zero_()
         ws["dxb"].zero_()
         C("cg_layernorm_bwd", P(ws["dy"]), P(ws["x_out"]), P(self.ln_post[0]), P(ws["meanp"]), P(ws["rstdp"]), n, D, T * D, 0, P(ws["dx"]), P(ws["dxb"]))
@@ -220,9 +273,7 @@ class VisionTransformerB200:
         C("cg_layernorm_bwd", P(ws["dx"]), P(ws["x0"]), P(self.ln_pre[0]), P(ws["mean0"]), P(ws["rstd0"]), M, D, D, 0, P(ws["dx0"]), None)
         C("cg_vit_tokens_to_bf16", P(ws["dx0"]), n, T, D, 1, P(ws["dtok"]))
         # fp32 output: this is the last rounding before the image gradient (the bf16 variant cost ~1e-3 of rel-L2 margin)
-        dpatch = torch.empty(n, g2, self.kpad, device=self.device, dtype=torch.float32)
-        gemm_bf16_tn(ws["dtok"], self.w_patch_t, _lib.EPI_F32, out=dpatch.view(n * g2, self.kpad))
-        return dpatch
+        gemm_bf16_tn(ws["dtok"], self.w_patch_t, _lib.EPI_F32, out=ws["dpatch"].view(n * g2, self.kpad))
 
     def flops_fwd_bwd(self, n):
         """Algorithmic FLOPs (2 x MAC) of forward + dgrad for n images."""

@@ -214,3 +214,29 @@ def test_stale_workspace_backward_raises_instead_of_wrong_gradients():
     eb = embed_image(mine, b)
     (gb2,) = torch.autograd.grad(eb.sum(), b)
     assert torch.equal(gb, gb2) and torch.isfinite(ga).all()
+
+
+def test_tower_cuda_graph_replay_equals_eager_launches():
+    """The tower captures its forward / backward pass into CUDA graphs on the second call of a batch size and replays them afterwards
+    (models.VisionTransformerB200._run_pass).  Same kernels on the same buffers: embeddings and patch gradients must be bit-identical
+    with a tower that issues every launch eagerly, for every call (eager first call, capture, replays) and two batch sizes."""
+    from clip_diffusion_b200 import models
+
+    name = "test-small/16"
+    models.register_clip_config(name, *TOWERS[name])
+    sd = models.random_clip_state_dict(name, seed=5)
+    graphed = models.CLIPModelB200(name, sd, "cuda").visual.tower
+    eager = models.CLIPModelB200(name, sd, "cuda").visual.tower
+    eager.use_graphs = False
+    assert graphed.use_graphs
+    g = torch.Generator().manual_seed(0)
+    for it in range(5):
+        for n in (3, 2):
+            patches = (torch.randn(n, graphed.grid ** 2, graphed.kpad, generator=g) * 0.5).bfloat16().cuda()
+            demb = torch.randn(n, graphed.output_dim, generator=g).cuda()
+            e1, e2 = graphed.forward_patches(patches), eager.forward_patches(patches)
+            assert torch.equal(e1, e2), (it, n)
+            d1, d2 = graphed.backward_patches(demb).clone(), eager.backward_patches(demb).clone()
+            assert torch.equal(d1, d2), (it, n)
+    st = graphed._ws[3]["graphs"]
+    assert st["fwd"]["graph"] is not None and st["bwd"]["graph"] is not None and not st["fwd"]["failed"] and not st["bwd"]["failed"]
