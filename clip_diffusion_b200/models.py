@@ -193,7 +193,8 @@ class VisionTransformerB200:
             k0, c0 = _lib.kernel_launches, _lib.launch_count
             graph = torch.cuda.CUDAGraph()
             try:
-                with torch.cuda.graph(graph):
+                # thread_local: other threads (NCCL watchdog, data loaders) may touch the CUDA API while this thread captures
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     body()
             except Exception as exc:  # keep the product path alive, loudly: the eager launches are the same kernels
                 import warnings
